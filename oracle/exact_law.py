@@ -1,0 +1,81 @@
+"""Test infrastructure only (oracle/): exact output laws on small graphs.
+
+`p_ref(dump, k)`  -- the reference UGS law of SURVEY.md section 0.1 / Appendix A.5-A.6:
+    P(S) = b[r]/Z * sum over growth orders of prod 1/|cut_i|, computed by exhaustive recursion over the
+    growth process of rand_grow (reference sampler.cpp:36-85) from every viable root (sampler.cpp:117-173).
+`connected_subsets(rows, k)` -- all connected induced k-subsets (the uniform law's support), the job the
+    reference's uniform_sampler does by C(n,k) enumeration (uniform_sampler.cpp).
+`p_epsilon(rows, k, eps)` -- the accepted-sample law of the epsilon_uniform sampler (Appendix A.9).
+Pure Python: small cases only.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from itertools import combinations
+
+
+def rows_from_dump(d):
+    n = len(d["order"])
+    return [list(map(int, d["indices"][int(d["indptr"][v]):int(d["indptr"][v + 1])])) for v in range(n)]
+
+
+def p_ref(d, k: int):
+    """dict {frozenset(S) (complete) or tuple (partial row): probability} under the reference law."""
+    rows = rows_from_dump(d)
+    n = len(rows)
+    index_of = [int(x) for x in d["index_of"]]
+    order = [int(x) for x in d["order"]]
+    b = [float(x) for x in d["bucket_b"]]
+    sd = [int(x) for x in d["suffix_deg"]]
+    Z = sum(b)
+    if Z > 0:
+        roots = {vi: b[vi] / Z for vi in range(n) if b[vi] > 0}
+    else:
+        el = [vi for vi in range(n) if sd[vi] > 0] or list(range(n))
+        roots = {vi: 1.0 / len(el) for vi in el}
+    out = defaultdict(float)
+
+    def rec(S, root_vi, p):
+        if len(S) == k:
+            out[frozenset(S)] += p
+            return
+        cut = sorted({w for u in S for w in rows[u] if index_of[w] >= root_vi and w not in S})
+        if not cut:
+            out[tuple(S)] += p  # partial row (only at relaxation levels 1/2)
+            return
+        for w in cut:
+            rec(S + [w], root_vi, p / len(cut))
+
+    for vi, pr in roots.items():
+        rec([order[vi]], vi, pr)
+    return dict(out)
+
+
+def connected_subsets(rows, k: int):
+    n = len(rows)
+    adj = [set(r) - {v} for v, r in enumerate(rows)]
+    res = []
+    for comb in combinations(range(n), k):
+        s = set(comb)
+        seen = {comb[0]}
+        stack = [comb[0]]
+        while stack:
+            u = stack.pop()
+            for w in adj[u]:
+                if w in s and w not in seen:
+                    seen.add(w)
+                    stack.append(w)
+        if len(seen) == k:
+            res.append(frozenset(comb))
+    return res
+
+
+def chi_square(counts: dict, law: dict, total: int):
+    """Pearson statistic, degrees of freedom, and #observations outside the law's support."""
+    stat = 0.0
+    for key, p in law.items():
+        e = p * total
+        o = counts.get(key, 0)
+        stat += (o - e) ** 2 / e
+    extra = sum(c for key, c in counts.items() if key not in law)
+    return stat, len(law) - 1, extra
