@@ -1,0 +1,154 @@
+/*
+ * ugs_b200.h -- C ABI of libugs_b200.so: the B200 (sm_100a) uniform k-graphlet sampler that replaces
+ * SS-GNN's `ugs_sampler` hot path (reference: src/samplers/ugs_sampler, v2.2.1).
+ *
+ * Plain pointers and sizes only: no torch types. All data pointers are DEVICE pointers unless a
+ * parameter is named h_*. Every entry point returns 0 on success or a negative UGS_E* code; the
+ * message is available from ugs_last_error() (thread-local). Nothing here synchronises the stream
+ * except ugs_batch_info(), which copies 64 bytes back to the host.
+ *
+ * Call sequence for one batch (what ugs_sampler.sample_batch does,
+ * reference ugs_sampler_batch_extension.cpp:77-300):
+ *
+ *   ugs_workspace_layout(E, G, NT, &L)                         host only, sizes the workspace
+ *   ugs_segment_batch(...)        A.1  columns -> graphs       replaces slice_and_renumber (:41-75)
+ *   ugs_batch_info(...)                host reads {unsorted, n_general, max_n_general, ...}
+ *   [ugs_segment_apply_perm(...)]      only when the columns are not graph-contiguous
+ *   ugs_preproc_batch(...)        A.2-A.5  CSR, order, suffix degrees, weights
+ *                                      replaces create_preproc (preproc.cpp:262-284) per graph
+ *   ugs_sample_batch(...)         A.5-A.6  roots + growth + per-sample edge counts + scan
+ *                                      replaces sample() (sampler.cpp:91-181) per graph
+ *   <host reads *d_total, allocates edge_index[2,Ebar], edge_src[Ebar]>
+ *   ugs_emit_edges(...)           A.7  induced-edge extraction + compaction
+ *                                      replaces sampler.cpp:205-280 and the batch driver's
+ *                                      post-processing (ugs_sampler_batch_extension.cpp:188-231)
+ *
+ * "A.n" refers to SURVEY.md Appendix A (exact semantics).
+ */
+#ifndef UGS_B200_H
+#define UGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGS_B200_ABI_VERSION 1
+
+/* error codes */
+#define UGS_OK 0
+#define UGS_EINVAL (-1)   /* bad argument (message says which) */
+#define UGS_ECUDA (-2)    /* CUDA runtime error */
+#define UGS_ELIMIT (-3)   /* input exceeds an implementation limit (k > 32, graph too large, ...) */
+
+/* edge modes: sample_batch mode "sample"/"graph"/"global"  ==  sample() edge_mode "local"/"flat"/"global"
+ * (reference ugs_sampler_batch_extension.cpp:170-174, sampler.cpp:258-280) */
+#define UGS_MODE_SAMPLE 0
+#define UGS_MODE_GRAPH 1
+#define UGS_MODE_GLOBAL 2
+
+/* sampler variants */
+#define UGS_VARIANT_REF 0      /* the reference law: root ~ b/Z, one rand_grow, no rejection (sampler.cpp:158-181) */
+#define UGS_VARIANT_UNIFORM 1  /* exact-uniform accept/reject on top of the same root/growth laws */
+
+#define UGS_MAX_K 32           /* general path; the bitmask fast path takes k <= 16 */
+#define UGS_SMALL_MAX_N 64     /* graphs with <= 64 nodes take the one-thread-per-sample bitmask path */
+#define UGS_SMALL_MAX_COLS 384 /* ... if they also have <= 384 edge columns */
+
+/* Byte offsets of every array inside the caller-allocated preprocessing workspace. The arrays are the
+ * device-resident equivalent of the reference's `struct Preproc` (sampler.hpp:81-93), stored once for the
+ * whole batch and indexed by batch-global node id (minus node_base) / CSR position. */
+typedef struct ugs_layout {
+    size_t total_bytes;
+    size_t cstart;     /* int64  [G+2]   column range of graph g: [cstart[g], cstart[g+1]) */
+    size_t ginfo;      /* ugs_ginfo [G]                                                    */
+    size_t glist;      /* int32  [G]     ids of the graphs on the general (warp-per-sample) path */
+    size_t counters;   /* int64  [16]    see UGS_CTR_*                                      */
+    size_t colkey;     /* int32  [E]     graph id of each column (G = belongs to no graph)  */
+    size_t rowptr;     /* uint32 [NT+G]  graph g: n+1 entries at (lo-node_base)+g, relative to 2*cstart[g] */
+    size_t order;      /* int32  [NT]    vertex (local id) at order position vi   (Preproc::order)      */
+    size_t index_of;   /* int32  [NT]    position of local vertex v                (Preproc::index_of)   */
+    size_t suffix_deg; /* int32  [NT]    by position                               (Preproc::suffix_deg) */
+    size_t bucket_b;   /* double [NT]    by position                               (Preproc::bucket_b)   */
+    size_t cum;        /* double [NT]    root-draw CDF by position (level 0: running sum of bucket_b)    */
+    size_t adj;        /* uint64 [NT]    adjacency bitmask (bitmask path only)                           */
+    size_t suf;        /* uint64 [NT]    by position: {v : index_of[v] >= vi} (bitmask path only)        */
+    size_t csr_idx;    /* int32  [2E]    neighbour local id                        (Preproc::indices)    */
+    size_t csr_col;    /* int32  [2E]    batch-global source column                (edge_col_of_csr_pos -> g_edge2global) */
+} ugs_layout;
+
+typedef struct ugs_ginfo {
+    double Z;            /* sum of bucket_b in position order (Preproc::Z)                           */
+    int32_t nnz;         /* CSR entries stored (get_preproc_info num_edges_stored)                   */
+    int32_t level;       /* relaxation level 0/1/2 (sampler.cpp:125-146); -1 if the graph is skipped */
+    int32_t n_eligible;  /* #root positions eligible at that level; level 0 = bucket_count_nonzero   */
+    int32_t last_viable; /* largest position with bucket_b > 0 (root-draw guard)                     */
+    int32_t mult;        /* >0: every adjacent pair appears exactly `mult` times per row, no self loops */
+    int32_t cls;         /* 0 = skipped (n <= 0 or n < k), 1 = bitmask path, 2 = general path        */
+} ugs_ginfo;
+
+/* counters[] slots */
+#define UGS_CTR_UNSORTED 0      /* !=0: columns are not graph-contiguous -> caller must sort (see below) */
+#define UGS_CTR_N_GENERAL 1
+#define UGS_CTR_MAX_N_GENERAL 2
+#define UGS_CTR_N_SKIPPED 3
+#define UGS_CTR_TOTAL_EDGES 4   /* written by ugs_sample_batch                                          */
+#define UGS_CTR_INCOMPLETE 5    /* rows with a -1                                                        */
+#define UGS_CTR_RELAXED 6       /* graphs sampled at relaxation level > 0                                */
+#define UGS_CTR_TRIALS 7        /* growth attempts (== samples for VARIANT_REF)                          */
+#define UGS_CTR_SCAN_TICKET 8
+
+int ugs_abi_version(void);
+const char* ugs_last_error(void);
+
+/* Sizes and offsets of the workspace for a batch with E columns, G graphs and NT = ptr[G]-ptr[0] nodes. */
+int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout* out);
+
+/* A.1 -- map every column to its graph, find per-graph column ranges, classify graphs.
+ * edge_index: [2,E] int64 row-major (row 1 at edge_index + E). ptr: [G+1] int64, non-decreasing.
+ * perm: NULL, or int64[E] = a stable ordering of the columns by graph id produced after a first call
+ * reported UGS_CTR_UNSORTED (columns are then read through perm).
+ * skip_lt_k: 1 = graphs with fewer than k nodes produce all -1 rows (sample_batch, :132-143);
+ *            0 = they are preprocessed and sampled at a relaxation level (handle API, sampler.cpp:125-146). */
+int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int k,
+                      int skip_lt_k, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream);
+
+/* Copies counters[0..7] to h_out (synchronises the stream). */
+int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
+
+/* A.2-A.5 -- per-graph CSR (multigraph, column order), (degree,id) order, suffix degrees, reachability,
+ * bucket weights, root CDF. n_general / max_n_general come from ugs_batch_info. */
+int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
+                      int k, const int64_t* perm, int64_t n_general, void* workspace, const ugs_layout* L,
+                      void* stream);
+
+/* Scratch bytes ugs_sample_batch needs for G*m samples. */
+size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);
+
+/* A.5-A.6 + counts. Writes nodes[G*m,k] (batch-global ids, -1 pad; lo is added for every mode exactly as the
+ * batch driver does, :188-196), edge_ptr[G*m+1] (exclusive running totals), sample_ptr[G+1] (= g*m, :130),
+ * counters[UGS_CTR_TOTAL_EDGES..]. Randomness: Philox4x32-10 keyed (seed; graph_index_base+g, sample i). */
+int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                     uint64_t graph_index_base, int variant, int64_t n_general, int64_t max_n_general,
+                     void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
+                     int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream);
+
+/* A.7 -- induced-edge emission for the node rows in `nodes` (normally the ones ugs_sample_batch wrote; any
+ * rows whose per-sample counts are in edge_ptr work, which is how the extraction stage is pinned against the
+ * reference's own samples). edge_index_out: [2,total] (row 1 at +total), edge_src_out: [total]. */
+int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode,
+                   int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                   const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                   void* stream);
+
+/* Per-sample induced-edge counts for caller-provided node rows (writes edge_ptr like ugs_sample_batch). */
+int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
+                    void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
+                    const int64_t* nodes, int64_t* edge_ptr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGS_B200_H */

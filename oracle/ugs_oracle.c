@@ -73,6 +73,7 @@ typedef struct {
     double Z;
     int level;        /* relaxation level 0/1/2 (sampler.cpp:125-146) */
     i64 n_eligible;   /* #roots eligible at that level */
+    i64 last_viable;  /* largest position with bucket_b > 0 */
     double* alias_prob;
     i32* alias_alias;
 } OPreproc;
@@ -222,13 +223,23 @@ static void build_alias(OPreproc* P) {
     free(p); free(small); free(large);
 }
 
-/* relaxation levels -- sampler.cpp:117-146 */
+/* relaxation levels -- sampler.cpp:117-146. For levels 1/2 the root CDF `cum` is re-expressed as the running
+ * count of eligible positions (level 1: suffix_deg > 0; level 2: every position), so that one CDF search
+ * serves every level (shared root-draw rule, see header). */
 static void compute_level(OPreproc* P) {
     i64 c0 = 0, c1 = 0;
     for (i64 vi = 0; vi < P->n; ++vi) { if (P->bucket_b[vi] > 0.0) c0++; if (P->suffix_deg[vi] > 0) c1++; }
+    P->last_viable = -1;
+    for (i64 vi = 0; vi < P->n; ++vi) if (P->bucket_b[vi] > 0.0) P->last_viable = vi;
     if (c0 > 0) { P->level = 0; P->n_eligible = c0; }
-    else if (c1 > 0) { P->level = 1; P->n_eligible = c1; }
-    else { P->level = 2; P->n_eligible = P->n; }
+    else if (c1 > 0) {
+        P->level = 1; P->n_eligible = c1;
+        i64 run = 0;
+        for (i64 vi = 0; vi < P->n; ++vi) { if (P->suffix_deg[vi] > 0) run++; P->cum[vi] = (double)run; }
+    } else {
+        P->level = 2; P->n_eligible = P->n;
+        for (i64 vi = 0; vi < P->n; ++vi) P->cum[vi] = (double)(vi + 1);
+    }
 }
 
 /* create_preproc -- preproc.cpp:262-284 */
@@ -278,23 +289,19 @@ void oracle_preproc_copy(const OPreproc* P, i64* indptr, i32* indices, i32* edge
  * ---------------------------------------------------------------------------------------------- */
 static i64 draw_root(const OPreproc* P, const u32 w[4]) {
     const i64 n = P->n;
+    double x;
     if (P->level == 0) {
         u64 u53 = ((((u64)w[0]) << 32) | (u64)w[1]) >> 11;
-        double x = ((double)u53 * (1.0 / 9007199254740992.0)) * P->Z;
-        /* smallest vi with cum[vi] > x (binary search; cum is non-decreasing) */
-        i64 lo = 0, hi = n - 1;
-        while (lo < hi) { i64 mid = (lo + hi) >> 1; if (P->cum[mid] > x) hi = mid; else lo = mid + 1; }
-        /* guard: x can round up to Z; fall back to the last position with b > 0 */
-        if (!(P->cum[lo] > x) || !(P->bucket_b[lo] > 0.0)) {
-            lo = n - 1; while (lo > 0 && !(P->bucket_b[lo] > 0.0)) lo--;
-        }
-        return lo;
+        x = ((double)u53 * (1.0 / 9007199254740992.0)) * P->Z;
+    } else {
+        x = (double)mulhi32(w[0], (u32)P->n_eligible); /* idx-th eligible position, uniform */
     }
-    u32 idx = mulhi32(w[0], (u32)P->n_eligible);
-    if (P->level == 2) return (i64)idx;
-    i64 seen = 0;
-    for (i64 vi = 0; vi < n; ++vi) if (P->suffix_deg[vi] > 0) { if (seen == (i64)idx) return vi; seen++; }
-    return n - 1;
+    /* smallest vi with cum[vi] > x (binary search; cum is non-decreasing) */
+    i64 lo = 0, hi = n - 1;
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (P->cum[mid] > x) hi = mid; else lo = mid + 1; }
+    /* guard: at level 0, x can round up to Z; fall back to the last position with b > 0 */
+    if (P->level == 0 && !(P->cum[lo] > x)) lo = P->last_viable;
+    return lo;
 }
 
 static int cmp_i32(const void* a, const void* b) { i32 x = *(const i32*)a, y = *(const i32*)b; return (x > y) - (x < y); }

@@ -1,0 +1,121 @@
+// ugs_common.cuh -- shared device helpers for libugs_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ugs_b200.h"
+
+typedef int64_t i64;
+typedef int32_t i32;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define FULL_MASK 0xffffffffu
+
+// Host-side error plumbing (defined in ugs_capi.cu)
+int ugs_set_error(int code, const char* fmt, ...);
+#define UGS_CUDA_CHECK(expr)                                                             \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return ugs_set_error(UGS_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+#define UGS_LAUNCH_CHECK(name)                                                           \
+    do {                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess)                                                           \
+            return ugs_set_error(UGS_ECUDA, "launch %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+// Typed views into the workspace.
+struct WS {
+    i64* cstart;
+    ugs_ginfo* ginfo;
+    i32* glist;
+    unsigned long long* counters;
+    i32* colkey;
+    u32* rowptr;
+    i32* order;
+    i32* index_of;
+    i32* suffix_deg;
+    double* bucket_b;
+    double* cum;
+    u64* adj;
+    u64* suf;
+    i32* csr_idx;
+    i32* csr_col;
+};
+
+static inline WS ws_views(void* base, const ugs_layout* L) {
+    char* b = (char*)base;
+    WS w;
+    w.cstart = (i64*)(b + L->cstart);
+    w.ginfo = (ugs_ginfo*)(b + L->ginfo);
+    w.glist = (i32*)(b + L->glist);
+    w.counters = (unsigned long long*)(b + L->counters);
+    w.colkey = (i32*)(b + L->colkey);
+    w.rowptr = (u32*)(b + L->rowptr);
+    w.order = (i32*)(b + L->order);
+    w.index_of = (i32*)(b + L->index_of);
+    w.suffix_deg = (i32*)(b + L->suffix_deg);
+    w.bucket_b = (double*)(b + L->bucket_b);
+    w.cum = (double*)(b + L->cum);
+    w.adj = (u64*)(b + L->adj);
+    w.suf = (u64*)(b + L->suf);
+    w.csr_idx = (i32*)(b + L->csr_idx);
+    w.csr_col = (i32*)(b + L->csr_col);
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter = (sample i, draw block, graph lo, graph hi), key = (seed lo, seed hi).
+// Replaces the reference's xorshift ThreadRNG (sampler.hpp:26-36) and its graph-independent
+// seeding (sampler.cpp:160-161). Bit-identical to oracle/ugs_oracle.c::philox4x32_10.
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+    u32 x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        u32 n0 = hi1 ^ c1 ^ k0;
+        u32 n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+// position (0-based) of the r-th (0-based) set bit of a 32-bit word; requires r < popc(m)
+__device__ __forceinline__ int select_bit32(u32 m, int r) {
+    int pos = 0;
+    int c = __popc(m & 0xffffu);
+    if (r >= c) { r -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);
+    if (r >= c) { r -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xfu);
+    if (r >= c) { r -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);
+    if (r >= c) { r -= c; pos += 2; m >>= 2; }
+    c = m & 1u;
+    if (r >= c) { pos += 1; }
+    return pos;
+}
+
+__device__ __forceinline__ int select_bit64(u64 m, int r) {
+    u32 lo = (u32)m;
+    int c = __popc(lo);
+    if (r < c) return select_bit32(lo, r);
+    return 32 + select_bit32((u32)(m >> 32), r - c);
+}
+
+// root-draw uniform in [0,1) * Z from two 32-bit words (53-bit mantissa), same arithmetic as the oracle
+__device__ __forceinline__ double root_x(u32 w0, u32 w1, double Z) {
+    u64 u53 = ((((u64)w0) << 32) | (u64)w1) >> 11;
+    return ((double)u53 * (1.0 / 9007199254740992.0)) * Z;
+}

@@ -1,0 +1,723 @@
+// ugs_sample.cu -- root draw, k-graphlet growth, induced-edge counting, scan and emission on sm_100a.
+//
+// Replaces, for the whole batch at once:
+//   sample()            sampler.cpp:91-181    roots (A.5) + rand_grow (sampler.cpp:36-85, A.6)
+//   edge extraction     sampler.cpp:205-280   (A.7) and the batch driver's concatenation / offsets
+//                       (ugs_sampler_batch_extension.cpp:188-231,257-290)
+// Bitmask path: one THREAD per sample, the graph's adjacency bitmasks / CSR staged in shared memory per warp.
+// General path: one WARP per sample, CSR read through L2, the cut kept as a per-warp bitmap in shared memory.
+// Both paths draw the same Philox words and pick the r-th smallest vertex id of the distinct cut, so they
+// (and oracle/ugs_oracle.c) produce identical samples.
+#include "ugs_common.cuh"
+
+#define SAMP_WARPS 8
+#define EMIT_WARPS 4
+#define EMIT_STAGE 2048  // staged edge entries per warp tile (32 samples)
+
+// =====================================================================================================
+// Bitmask path: sample + count
+// =====================================================================================================
+struct __align__(16) SmallSamp {
+    u64 adj[64];
+    u64 suf[64];
+    double cum[64];
+    unsigned char tile[32][16];
+    unsigned short rowptr[66];
+    unsigned char order[64];
+    unsigned char idx[2 * UGS_SMALL_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
+               int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
+               i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
+    __shared__ SmallSamp sm_all[SAMP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 item = (i64)blockIdx.x * SAMP_WARPS + warp;
+    const i64 g = item / items_per_graph;
+    if (g >= G) return;
+    const int chunk = (int)(item - g * items_per_graph);
+    if (chunk == 0 && lane == 0) {
+        sample_ptr[g + 1] = (g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
+        if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
+    }
+    const ugs_ginfo gi = w.ginfo[g];
+    if (gi.cls == 2) return;
+    const int ntiles = (int)((m + 31) >> 5);
+    const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
+    const i64 lo = ptr[g];
+    const int r32 = 32 % k, q32 = 32 / k;
+
+    if (gi.cls == 0) {  // n <= 0 or n < k: m rows of -1, no edges (:132-143)
+        for (int t = t0; t < t1; ++t) {
+            const i64 s0 = g * m + (i64)t * 32;
+            const int nv = (int)min((i64)32, m - (i64)t * 32);
+            for (int e = lane; e < nv * k; e += 32) nodes_out[s0 * k + e] = -1;
+            if (lane < nv) edge_ptr[1 + s0 + lane] = 0;
+        }
+        return;
+    }
+
+    SmallSamp& s = sm_all[warp];
+    const int n = (int)(ptr[g + 1] - lo);
+    const i64 nb = lo - node_base;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < n) {
+            s.adj[v] = w.adj[nb + v];
+            s.suf[v] = w.suf[nb + v];
+            s.cum[v] = w.cum[nb + v];
+            s.order[v] = (unsigned char)w.order[nb + v];
+        }
+    }
+    if (gi.mult == 0) {  // irregular multiplicities / self loops: counts need the CSR rows
+        const u32* rp = w.rowptr + nb + g;
+        const i32* ci = w.csr_idx + 2 * w.cstart[g];
+        for (int v = lane; v <= n; v += 32) s.rowptr[v] = (unsigned short)rp[v];
+        for (int p = lane; p < gi.nnz; p += 32) s.idx[p] = (unsigned char)ci[p];
+    }
+    __syncwarp();
+
+    const u64 gidx = gbase + (u64)g;
+    const u32 c2 = (u32)gidx, c3 = (u32)(gidx >> 32), k0 = (u32)seed, k1 = (u32)(seed >> 32);
+    int n_incomplete = 0;
+
+    for (int t = t0; t < t1; ++t) {
+        const i64 i = (i64)t * 32 + lane;  // sample index inside the graph
+        const bool active = i < m;
+        u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
+        i64 cnt = 0;
+        if (active) {
+            Philox4 r = philox4x32_10((u32)i, 0u, c2, c3, k0, k1);
+            // ---- root (A.5) ------------------------------------------------------------------------
+            const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z)
+                                             : (double)__umulhi(r.x, (u32)gi.n_eligible);
+            int a = 0, b = n - 1;
+            while (a < b) {
+                const int mid = (a + b) >> 1;
+                if (s.cum[mid] > x) b = mid; else a = mid + 1;
+            }
+            if (gi.level == 0 && !(s.cum[a] > x)) a = gi.last_viable;
+            const int root_vi = a;
+            // ---- growth (A.6) ----------------------------------------------------------------------
+            const int v0 = s.order[root_vi];
+            const u64 sufm = s.suf[root_vi];
+            u64 S = 1ull << v0;
+            u64 nbr = s.adj[v0];
+            nlo = (nlo & ~0xFFull) | (u64)v0;
+            int size = 1;
+            for (int step = 1; step < k; ++step) {
+                const u64 cut = nbr & sufm & ~S;
+                const int c = __popcll(cut);
+                if (c == 0) break;
+                const int wsel = (step + 1) & 3;
+                if (wsel == 0) r = philox4x32_10((u32)i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
+                const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
+                const int xnew = select_bit64(cut, (int)__umulhi(wv, (u32)c));
+                S |= 1ull << xnew;
+                nbr |= s.adj[xnew];
+                if (step < 8) nlo = (nlo & ~(0xFFull << (8 * step))) | ((u64)xnew << (8 * step));
+                else nhi = (nhi & ~(0xFFull << (8 * (step - 8)))) | ((u64)xnew << (8 * (step - 8)));
+                size++;
+            }
+            // ---- induced-edge count (A.7) ------------------------------------------------------------
+            if (size == k) {
+                if (gi.mult > 0) {
+                    int c = 0;
+                    for (int j = 0; j < k; ++j) {
+                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                        c += __popcll(s.adj[v] & S);
+                    }
+                    cnt = (i64)c * gi.mult;
+                } else {
+                    int c = 0;
+                    for (int j = 0; j < k; ++j) {
+                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                        for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & 1ull);
+                    }
+                    cnt = c;
+                }
+            } else {
+                n_incomplete++;
+            }
+        }
+        // ---- coalesced output through the shared tile ------------------------------------------------
+        *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
+        __syncwarp();
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+        {
+            int sidx = lane / k, j = lane - sidx * k;
+            i64* out = nodes_out + s0 * k;
+            for (int e = lane; e < nv * k; e += 32) {
+                const unsigned char bv = s.tile[sidx][j];
+                out[e] = (bv == 0xFF) ? (i64)-1 : lo + (i64)bv;  // batch ext :194 adds lo
+                j += r32; sidx += q32;
+                if (j >= k) { j -= k; sidx++; }
+            }
+        }
+        if (active) edge_ptr[1 + s0 + lane] = cnt;
+        __syncwarp();
+    }
+    // statistics (the only cross-rank exchange later all-gathers these)
+    n_incomplete = __reduce_add_sync(FULL_MASK, n_incomplete);
+    if (lane == 0) {
+        if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
+        if (chunk == 0 && gi.level > 0) atomicAdd(&w.counters[UGS_CTR_RELAXED], 1ull);
+    }
+}
+
+// =====================================================================================================
+// General path: one warp per sample
+// =====================================================================================================
+// Is x one of the first `size` members held one per lane in `mine`?
+__device__ __forceinline__ bool in_members(int x, int mine, int size) {
+    bool hit = false;
+    for (int j = 0; j < size; ++j) {
+        const int mj = __shfl_sync(FULL_MASK, mine, j);  // every lane must take part (no short-circuit)
+        hit = hit || (x == mj);
+    }
+    return hit;
+}
+
+__global__ void __launch_bounds__(256)
+k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
+                 i64 n_general, int bm_words, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr) {
+    extern __shared__ u32 bm_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    u32* bm = bm_all + (size_t)warp * bm_words;
+    for (int i = lane; i < bm_words; i += 32) bm[i] = 0;
+    __syncwarp();
+    const u32 lt_mask = (1u << lane) - 1u;
+    const i64 total = n_general * m;
+    const i64 nwarps = (i64)gridDim.x * wpb;
+    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+    unsigned long long n_incomplete = 0, n_relaxed = 0;
+
+    for (i64 t = (i64)blockIdx.x * wpb + warp; t < total; t += nwarps) {
+        const i64 gi_ = t / m;
+        const i64 i = t - gi_ * m;
+        const i64 g = w.glist[gi_];
+        const ugs_ginfo gi = w.ginfo[g];
+        const i64 lo = ptr[g];
+        const int n = (int)(ptr[g + 1] - lo);
+        const i64 nb = lo - node_base;
+        const u32* rp = w.rowptr + nb + g;
+        const i32* ord = w.order + nb;
+        const i32* iof = w.index_of + nb;
+        const double* cm = w.cum + nb;
+        const i32* cidx = w.csr_idx + 2 * w.cstart[g];
+        const u64 gidx = gbase + (u64)g;
+        const u32 c2 = (u32)gidx, c3 = (u32)(gidx >> 32);
+        if (i == 0 && gi.level > 0) n_relaxed++;
+
+        Philox4 r = philox4x32_10((u32)i, 0u, c2, c3, k0, k1);
+        const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
+        int a = 0, b = n - 1;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (cm[mid] > x) b = mid; else a = mid + 1;
+        }
+        if (gi.level == 0 && !(cm[a] > x)) a = gi.last_viable;
+        const int root_vi = a;
+
+        int mine = -1;  // lane j holds S[j]
+        int size = 0;
+        int cutn = 0;
+        int xnew = ord[root_vi];
+        const int words = (n + 31) >> 5;
+        for (int step = 0; step < k; ++step) {
+            if (step > 0) {
+                if (cutn == 0) break;
+                const int wsel = (step + 1) & 3;
+                if (wsel == 0) r = philox4x32_10((u32)i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
+                const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
+                int rsel = (int)__umulhi(wv, (u32)cutn);
+                // r-th set bit of the cut bitmap (ascending vertex id)
+                xnew = -1;
+                for (int wb = 0; wb < words; wb += 32) {
+                    const int wi = wb + lane;
+                    const u32 word = (wi < words) ? bm[wi] : 0u;
+                    const int c = __popc(word);
+                    int incl = c;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int y = __shfl_up_sync(FULL_MASK, incl, off);
+                        if (lane >= off) incl += y;
+                    }
+                    const int tot = __shfl_sync(FULL_MASK, incl, 31);
+                    if (rsel < tot) {
+                        const u32 ball = __ballot_sync(FULL_MASK, incl > rsel);
+                        const int src = __ffs(ball) - 1;
+                        const int excl_src = __shfl_sync(FULL_MASK, incl - c, src);
+                        const u32 word_src = __shfl_sync(FULL_MASK, word, src);
+                        xnew = (wb + src) * 32 + select_bit32(word_src, rsel - excl_src);
+                        break;
+                    }
+                    rsel -= tot;
+                }
+                if (xnew < 0) break;  // cannot happen: cutn counts the set bits
+                if (lane == 0) bm[xnew >> 5] &= ~(1u << (xnew & 31));
+                cutn--;
+                __syncwarp();
+            }
+            if (lane == size) mine = xnew;
+            size++;
+            // add row(xnew) to the cut: suffix members not in S and not yet in the cut
+            const u32 p0 = rp[xnew], p1 = rp[xnew + 1];
+            for (u32 pb = p0; pb < p1; pb += 32) {
+                const u32 p = pb + lane;
+                int y = -1;
+                bool ok = false;
+                if (p < p1) { y = cidx[p]; ok = (iof[y] >= root_vi); }
+                const bool member = in_members(y, mine, size);  // warp-wide: evaluate before combining
+                ok = ok && !member;
+                bool isnew = false;
+                if (ok) {
+                    const u32 bit = 1u << (y & 31);
+                    const u32 old = atomicOr(&bm[y >> 5], bit);
+                    isnew = (old & bit) == 0;
+                }
+                cutn += __popc(__ballot_sync(FULL_MASK, isnew));
+            }
+            __syncwarp();
+        }
+        // ---- clear the bitmap and count induced entries in one more pass over the rows of S ----------
+        int cntE = 0;
+        for (int j = 0; j < size; ++j) {
+            const int u = __shfl_sync(FULL_MASK, mine, j);
+            const u32 p0 = rp[u], p1 = rp[u + 1];
+            for (u32 pb = p0; pb < p1; pb += 32) {
+                const u32 p = pb + lane;
+                int y = -1;
+                if (p < p1) { y = cidx[p]; bm[y >> 5] = 0u; }
+                const bool hit = in_members(y, mine, size) && (p < p1);
+                cntE += __popc(__ballot_sync(FULL_MASK, hit));
+            }
+        }
+        __syncwarp();
+        const i64 sidx = g * m + i;
+        if (lane < k) nodes_out[sidx * k + lane] = (lane < size) ? lo + (i64)mine : (i64)-1;
+        if (lane == 0) {
+            edge_ptr[1 + sidx] = (size == k) ? (i64)cntE : 0;
+            if (size < k) n_incomplete++;
+        }
+        (void)lt_mask;
+    }
+    if (lane == 0) {
+        if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], n_incomplete);
+        if (n_relaxed) atomicAdd(&w.counters[UGS_CTR_RELAXED], n_relaxed);
+    }
+}
+
+// =====================================================================================================
+// In-place inclusive scan of the per-sample counts (single pass, decoupled look-back)
+// =====================================================================================================
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ scratch,
+              unsigned long long* __restrict__ counters) {
+    __shared__ i64 s_warp[SCAN_THREADS / 32];
+    __shared__ i64 s_prefix;
+    __shared__ unsigned int s_tile;
+    unsigned long long* ticket = scratch;
+    volatile unsigned long long* status = scratch + 1;
+    if (threadIdx.x == 0) s_tile = (unsigned int)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const i64 tile = s_tile;
+    const i64 base = tile * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+    i64 v[SCAN_ITEMS];
+    i64 local = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+        v[q] = (base + q < B) ? data[base + q] : 0;
+        local += v[q];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    i64 incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const i64 y = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    i64 warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_THREADS / 32; ++q) {
+        const i64 x = s_warp[q];
+        if (q < warp) warp_excl += x;
+        block_total += x;
+    }
+    if (threadIdx.x == 0) {
+        i64 prefix = 0;
+        if (tile == 0) {
+            status[0] = ((unsigned long long)block_total << 2) | 2ull;
+        } else {
+            status[tile] = ((unsigned long long)block_total << 2) | 1ull;
+            __threadfence();
+            i64 j = tile - 1;
+            while (true) {
+                unsigned long long sv = status[j];
+                while ((sv & 3ull) == 0ull) sv = status[j];
+                prefix += (i64)(sv >> 2);
+                if ((sv & 3ull) == 2ull) break;
+                --j;
+            }
+            status[tile] = ((unsigned long long)(prefix + block_total) << 2) | 2ull;
+        }
+        s_prefix = prefix;
+        if ((tile + 1) * SCAN_TILE >= B) counters[UGS_CTR_TOTAL_EDGES] = (unsigned long long)(prefix + block_total);
+    }
+    __syncthreads();
+    i64 run = s_prefix + warp_excl + (incl - local);
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+        run += v[q];
+        if (base + q < B) data[base + q] = run;
+    }
+}
+
+// =====================================================================================================
+// Bitmask path: emission with shared-memory staging and coalesced stores
+// =====================================================================================================
+struct __align__(16) SmallEmit {
+    u32 stage[EMIT_STAGE];
+    i32 col[2 * UGS_SMALL_MAX_COLS];
+    unsigned char tile[32][16];
+    unsigned short rowptr[66];
+    unsigned char idx[2 * UGS_SMALL_MAX_COLS];
+};
+
+__device__ __forceinline__ int find_local(u64 nlo, u64 nhi, int x) {
+    const u32 pat = (u32)x * 0x01010101u;
+    u32 m0 = __vcmpeq4((u32)nlo, pat);
+    if (m0) return (__ffs(m0) - 1) >> 3;
+    m0 = __vcmpeq4((u32)(nlo >> 32), pat);
+    if (m0) return 4 + ((__ffs(m0) - 1) >> 3);
+    m0 = __vcmpeq4((u32)nhi, pat);
+    if (m0) return 8 + ((__ffs(m0) - 1) >> 3);
+    m0 = __vcmpeq4((u32)(nhi >> 32), pat);
+    return 12 + ((__ffs(m0) - 1) >> 3);
+}
+
+__global__ void __launch_bounds__(EMIT_WARPS * 32)
+k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
+             i64 items_per_graph, WS w, const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr,
+             i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
+    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
+    SmallEmit* sm_all = reinterpret_cast<SmallEmit*>(emit_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
+    const i64 g = item / items_per_graph;
+    if (g >= G) return;
+    const ugs_ginfo gi = w.ginfo[g];
+    if (gi.cls != 1 || gi.nnz == 0) return;
+    const int chunk = (int)(item - g * items_per_graph);
+    const int ntiles = (int)((m + 31) >> 5);
+    const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
+    if (t0 >= t1) return;
+    const i64 lo = ptr[g];
+    const int n = (int)(ptr[g + 1] - lo);
+    const i64 nb = lo - node_base;
+    // nothing to do if this item's samples emit no entries
+    {
+        const i64 sA = g * m + (i64)t0 * 32, sB = min(g * m + m, g * m + (i64)t1 * 32);
+        if (edge_ptr[sA] == edge_ptr[sB]) return;
+    }
+    SmallEmit& s = sm_all[warp];
+    {
+        const u32* rp = w.rowptr + nb + g;
+        const i64 cb = 2 * w.cstart[g];
+        for (int v = lane; v <= n; v += 32) s.rowptr[v] = (unsigned short)rp[v];
+        for (int p = lane; p < gi.nnz; p += 32) {
+            s.idx[p] = (unsigned char)w.csr_idx[cb + p];
+            s.col[p] = w.csr_col[cb + p];
+        }
+    }
+    const int r32 = 32 % k, q32 = 32 / k;
+
+    for (int t = t0; t < t1; ++t) {
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+        __syncwarp();
+        // node rows -> shared tile (coalesced read)
+        {
+            int sidx = lane / k, j = lane - sidx * k;
+            const i64* in = nodes + s0 * k;
+            for (int e = lane; e < nv * k; e += 32) {
+                const i64 val = in[e];
+                s.tile[sidx][j] = (val < 0) ? (unsigned char)0xFF : (unsigned char)(val - lo);
+                j += r32; sidx += q32;
+                if (j >= k) { j -= k; sidx++; }
+            }
+        }
+        const i64 my_lo = (lane < nv) ? edge_ptr[s0 + lane] : 0;
+        const i64 tile_end = edge_ptr[s0 + nv];
+        const i64 tile_base = __shfl_sync(FULL_MASK, my_lo, 0);
+        const int tile_total = (int)min(tile_end - tile_base, (i64)0x7fffffff);
+        __syncwarp();
+        if (tile_total == 0) continue;
+        const bool staged = tile_total <= EMIT_STAGE;
+        if (lane < nv) {
+            const ulonglong2 nn = *reinterpret_cast<const ulonglong2*>(&s.tile[lane][0]);
+            const u64 nlo = nn.x, nhi = nn.y;
+            u64 S = 0;
+            bool complete = true;
+            for (int j = 0; j < k; ++j) {
+                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                if (v == 0xFF) complete = false; else S |= 1ull << v;
+            }
+            if (complete) {  // incomplete rows emit nothing (sampler.cpp:220-223)
+                i64 off = my_lo - tile_base;
+                const i64 i_in_graph = (i64)t * 32 + lane;
+                for (int j = 0; j < k; ++j) {
+                    const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                    const int pe = s.rowptr[v + 1];
+                    for (int p = s.rowptr[v]; p < pe; ++p) {
+                        const int x = s.idx[p];
+                        if ((S >> x) & 1ull) {
+                            const int l = find_local(nlo, nhi, x);
+                            if (staged) {
+                                s.stage[off] = (u32)j | ((u32)l << 5) | ((u32)lane << 10) | ((u32)p << 15);
+                            } else {
+                                i64 a, b;
+                                if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
+                                else if (mode == UGS_MODE_GRAPH) { a = i_in_graph * k + j; b = i_in_graph * k + l; }
+                                else { a = lo + v; b = lo + x; }
+                                const i64 o = tile_base + off;
+                                if (o < total) { out_u[o] = a; out_v[o] = b; out_src[o] = (i64)s.col[p]; }
+                            }
+                            off++;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (staged) {
+            for (int e = lane; e < tile_total; e += 32) {
+                const u32 pk = s.stage[e];
+                const int j = pk & 31, l = (pk >> 5) & 31, sl = (pk >> 10) & 31, p = pk >> 15;
+                i64 a, b;
+                if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
+                else if (mode == UGS_MODE_GRAPH) {
+                    const i64 ik = ((i64)t * 32 + sl) * k;
+                    a = ik + j; b = ik + l;
+                } else { a = lo + s.tile[sl][j]; b = lo + s.tile[sl][l]; }
+                const i64 o = tile_base + e;
+                if (o < total) {
+                    out_u[o] = a;
+                    out_v[o] = b;
+                    out_src[o] = (i64)s.col[p];
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// General path: emission, one warp per sample (also the generic counter for caller-provided rows)
+// =====================================================================================================
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(256)
+k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mode, i64 n_items, bool use_glist,
+               WS w, const i64* __restrict__ nodes, i64* __restrict__ edge_ptr, i64 total,
+               i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    const i64 nwarps = (i64)gridDim.x * wpb;
+    const i64 total_items = n_items * m;
+    for (i64 t = (i64)blockIdx.x * wpb + warp; t < total_items; t += nwarps) {
+        const i64 gi_ = t / m;
+        const i64 i = t - gi_ * m;
+        const i64 g = use_glist ? (i64)w.glist[gi_] : gi_;
+        const i64 sidx = g * m + i;
+        const ugs_ginfo gi = w.ginfo[g];
+        if (COUNT_ONLY && gi.cls == 0) { if (lane == 0) edge_ptr[1 + sidx] = 0; continue; }
+        i64 base = 0;
+        if (!COUNT_ONLY) {
+            base = edge_ptr[sidx];
+            if (edge_ptr[sidx + 1] == base) continue;
+        }
+        const i64 lo = ptr[g];
+        const i64 nb = lo - node_base;
+        const u32* rp = w.rowptr + nb + g;
+        const i32* cidx = w.csr_idx + 2 * w.cstart[g];
+        const i32* ccol = w.csr_col + 2 * w.cstart[g];
+        const i64 nv = (lane < k) ? nodes[sidx * k + lane] : 0;
+        const bool complete = !__any_sync(FULL_MASK, (lane < k) && nv < 0);
+        const int mine = (lane < k && nv >= 0) ? (int)(nv - lo) : -1;
+        i64 cnt = 0;
+        if (complete) {
+            for (int j = 0; j < k; ++j) {
+                const int u = __shfl_sync(FULL_MASK, mine, j);
+                const u32 p0 = rp[u], p1 = rp[u + 1];
+                for (u32 pb = p0; pb < p1; pb += 32) {
+                    const u32 p = pb + lane;
+                    int y = -2, l = -1;
+                    if (p < p1) y = cidx[p];
+                    for (int q = 0; q < k; ++q) if (y == __shfl_sync(FULL_MASK, mine, q)) l = q;
+                    const bool hit = (l >= 0) && (p < p1);
+                    const u32 ball = __ballot_sync(FULL_MASK, hit);
+                    if (!COUNT_ONLY && hit) {
+                        const i64 o = base + cnt + __popc(ball & lt_mask);
+                        i64 a, b;
+                        if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
+                        else if (mode == UGS_MODE_GRAPH) { a = i * k + j; b = i * k + l; }
+                        else { a = lo + u; b = lo + y; }
+                        if (o < total) { out_u[o] = a; out_v[o] = b; out_src[o] = (i64)ccol[p]; }
+                    }
+                    cnt += __popc(ball);
+                }
+            }
+        }
+        if (COUNT_ONLY && lane == 0) edge_ptr[1 + sidx] = cnt;
+    }
+}
+
+// =====================================================================================================
+// Host launchers
+// =====================================================================================================
+static int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+extern "C" size_t ugs_sample_scratch_bytes(int64_t G, int64_t m) {
+    const int64_t B = (G > 0 && m > 0) ? G * m : 0;
+    const int64_t tiles = (B + SCAN_TILE - 1) / SCAN_TILE + 1;
+    return (size_t)(tiles + 1) * sizeof(unsigned long long);
+}
+
+static int run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& w, cudaStream_t st) {
+    const size_t need = ugs_sample_scratch_bytes(B, 1);
+    if (scratch_bytes < need || !scratch) return ugs_set_error(UGS_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, need);
+    UGS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need, st));
+    if (B > 0) {
+        const i64 tiles = (B + SCAN_TILE - 1) / SCAN_TILE;
+        k_scan_counts<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(edge_ptr + 1, B, (unsigned long long*)scratch, w.counters);
+        UGS_LAUNCH_CHECK("k_scan_counts");
+    }
+    return UGS_OK;
+}
+
+static inline void small_items(int64_t m, int* tiles_per_item, int64_t* items_per_graph) {
+    const int64_t ntiles = (m + 31) / 32;
+    int tpi = (int)(ntiles < 4 ? (ntiles < 1 ? 1 : ntiles) : 4);
+    *tiles_per_item = tpi;
+    *items_per_graph = (ntiles + tpi - 1) / tpi;
+    if (*items_per_graph < 1) *items_per_graph = 1;
+}
+
+extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                                uint64_t graph_index_base, int variant, int64_t n_general, int64_t max_n_general,
+                                void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
+                                int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream_) {
+    if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
+    if (m < 0) return ugs_set_error(UGS_EINVAL, "m_per_graph must be >= 0");
+    if (variant != UGS_VARIANT_REF) return ugs_set_error(UGS_EINVAL, "unknown variant %d", variant);
+    if (m >= (1ll << 32)) return ugs_set_error(UGS_ELIMIT, "m_per_graph must be < 2^32");
+    cudaStream_t st = (cudaStream_t)stream_;
+    WS w = ws_views(workspace, L);
+    UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64) * 4, st));
+    if (G <= 0 || m == 0) {
+        // sample_ptr = arange * m; edge_ptr = [0]
+        UGS_CUDA_CHECK(cudaMemsetAsync(edge_ptr, 0, sizeof(i64), st));
+        UGS_CUDA_CHECK(cudaMemsetAsync(sample_ptr, 0, sizeof(i64) * (size_t)((G > 0 ? G : 0) + 1), st));
+        UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64), st));
+        return UGS_OK;
+    }
+    if (!nodes) return ugs_set_error(UGS_EINVAL, "nodes is NULL");
+    int tpi; int64_t ipg;
+    small_items(m, &tpi, &ipg);
+    {
+        const int64_t items = G * ipg;
+        k_sample_small<<<(unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS), SAMP_WARPS * 32, 0, st>>>(
+            ptr, G, node_base, m, k, seed, graph_index_base, tpi, ipg, w, nodes, edge_ptr, sample_ptr);
+        UGS_LAUNCH_CHECK("k_sample_small");
+    }
+    if (n_general > 0) {
+        const int bm_words = (int)((max_n_general + 31) / 32);
+        const size_t smem_cap = 200 * 1024;
+        int wpb = 8;
+        while (wpb > 1 && (size_t)wpb * bm_words * 4 > smem_cap) wpb >>= 1;
+        const size_t smem = (size_t)wpb * bm_words * 4;
+        if (smem > smem_cap)
+            return ugs_set_error(UGS_ELIMIT, "graph with %lld nodes exceeds the per-warp cut bitmap (max %zu nodes)",
+                                 (long long)max_n_general, smem_cap * 8);
+        UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        const int64_t total = n_general * m;
+        int64_t blocks = (total + wpb - 1) / wpb;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        k_sample_general<<<(unsigned)blocks, wpb * 32, smem, st>>>(ptr, node_base, m, k, seed, graph_index_base,
+                                                                  n_general, bm_words, w, nodes, edge_ptr);
+        UGS_LAUNCH_CHECK("k_sample_general");
+    }
+    return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
+}
+
+extern "C" int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
+                               void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
+                               const int64_t* nodes, int64_t* edge_ptr, void* stream_) {
+    if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
+    cudaStream_t st = (cudaStream_t)stream_;
+    WS w = ws_views(workspace, L);
+    UGS_CUDA_CHECK(cudaMemsetAsync(edge_ptr, 0, sizeof(i64), st));
+    if (G <= 0 || m <= 0) {
+        UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64), st));
+        return UGS_OK;
+    }
+    int64_t blocks = (G * m + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k_emit_general<true><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, 0, G, false, w, nodes, edge_ptr, 0,
+                                                          nullptr, nullptr, nullptr);
+    UGS_LAUNCH_CHECK("k_count_general");
+    (void)n_general;
+    return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
+}
+
+extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode,
+                              int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                              const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                              void* stream_) {
+    if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    if (mode < 0 || mode > 2) return ugs_set_error(UGS_EINVAL, "mode must be one of: 'sample', 'graph', 'global'");
+    if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
+    if (G <= 0 || m <= 0 || total <= 0) return UGS_OK;
+    if (!nodes || !edge_index_out || !edge_src_out) return ugs_set_error(UGS_EINVAL, "NULL output");
+    cudaStream_t st = (cudaStream_t)stream_;
+    WS w = ws_views(const_cast<void*>(workspace), L);
+    i64* out_u = edge_index_out;
+    i64* out_v = edge_index_out + total;
+    if (n_general < G) {
+        int tpi; int64_t ipg;
+        small_items(m, &tpi, &ipg);
+        const int64_t items = G * ipg;
+        const size_t smem = sizeof(SmallEmit) * EMIT_WARPS;
+        UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_emit_small<<<(unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS), EMIT_WARPS * 32, smem, st>>>(
+            ptr, G, node_base, m, k, mode, tpi, ipg, w, nodes, edge_ptr, total, out_u, out_v, edge_src_out);
+        UGS_LAUNCH_CHECK("k_emit_small");
+    }
+    if (n_general > 0) {
+        int64_t blocks = (n_general * m + 7) / 8;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        k_emit_general<false><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, mode, n_general, true, w, nodes,
+                                                               const_cast<i64*>(edge_ptr), total, out_u, out_v,
+                                                               edge_src_out);
+        UGS_LAUNCH_CHECK("k_emit_general");
+    }
+    return UGS_OK;
+}

@@ -1,0 +1,83 @@
+"""ctypes binding of libugs_b200.so (the C ABI declared in include/ugs_b200.h) and its nvcc build."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+REPO = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+SO = os.path.join(HERE, "libugs_b200.so")
+SOURCES = ["ugs_preproc.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_capi.cu"]
+HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
+
+EXPORTS = [
+    "ugs_abi_version", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
+    "ugs_preproc_batch", "ugs_sample_scratch_bytes", "ugs_sample_batch", "ugs_emit_edges", "ugs_count_edges",
+]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class Layout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_size_t) for n in (
+        "total_bytes", "cstart", "ginfo", "glist", "counters", "colkey", "rowptr", "order", "index_of",
+        "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col")]
+
+
+def nvcc_command(out: str = SO):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", f"-I{os.path.join(REPO, 'include')}",
+            f"-I{CSRC}"] + srcs + ["-o", out]
+
+
+def build(force: bool = False) -> str:
+    """Compile libugs_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))] + HEADERS
+    stale = (not os.path.exists(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(nvcc_command())
+    return SO
+
+
+_LIB = None
+
+
+def lib():
+    """Load the shared library. There is no CPU fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO):
+        raise LibraryMissing(
+            f"{SO} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The B200 sampler has no CPU fallback.")
+    L = ctypes.CDLL(SO)
+    vp, i64, u64, sz, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
+    LP = ctypes.POINTER(Layout)
+    L.ugs_abi_version.restype = ci
+    L.ugs_last_error.restype = ctypes.c_char_p
+    L.ugs_workspace_layout.argtypes = [i64, i64, i64, LP]
+    L.ugs_segment_batch.argtypes = [vp, i64, vp, i64, ci, ci, vp, vp, LP, vp]
+    L.ugs_batch_info.argtypes = [vp, LP, vp, vp]
+    L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, vp, LP, vp]
+    L.ugs_sample_scratch_bytes.restype = sz
+    L.ugs_sample_scratch_bytes.argtypes = [i64, i64]
+    L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
+    L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
+    L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
+    for name in dir(L):
+        pass
+    _LIB = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().ugs_last_error().decode("utf-8", "replace")
+        raise RuntimeError(msg or f"libugs_b200 error {rc}")

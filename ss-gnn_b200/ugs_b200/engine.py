@@ -1,0 +1,181 @@
+"""Device pipeline for one PyG batch: segment -> preprocess -> sample -> scan -> emit.
+
+Mirrors the reference batch driver (ugs_sampler_batch_extension.cpp:77-300) but runs every stage for the
+whole batch at once through libugs_b200.so. PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+MODES = {"sample": 0, "graph": 1, "global": 2}
+VARIANTS = {"ref": 0, "uniform": 1}
+CTR = dict(unsorted=0, n_general=1, max_n_general=2, n_skipped=3, total_edges=4, incomplete=5, relaxed=6, trials=7)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceBatch:
+    """Device-resident preprocessing of a batch of graphs: the equivalent of one reference `Preproc`
+    (sampler.hpp:81-93) per graph, built by three kernels for the whole batch.
+
+    edge_index: cuda int64 [2,E]; ptr: cuda int64 [G+1] (non-decreasing); node_base = ptr[0] and
+    total_nodes = ptr[G]-ptr[0] must be passed by the caller (known on the host), so that no device->host
+    read of ptr is needed.
+    """
+
+    def __init__(self, edge_index: torch.Tensor, ptr: torch.Tensor, k: int, node_base: int, total_nodes: int,
+                 skip_lt_k: bool = True):
+        L = _lib.lib()
+        if not (edge_index.is_cuda and ptr.is_cuda):
+            raise RuntimeError("DeviceBatch needs CUDA tensors (there is no CPU path)")
+        if edge_index.dtype != torch.int64:
+            raise RuntimeError("edge_index must be int64")
+        if ptr.dtype != torch.int64:
+            raise RuntimeError("ptr must be int64")
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise RuntimeError("edge_index must have shape [2, E]")
+        self.edge_index = edge_index.contiguous()
+        self.ptr = ptr.contiguous()
+        self.k = int(k)
+        self.E = int(edge_index.size(1))
+        self.G = int(ptr.numel()) - 1
+        self.node_base = int(node_base)
+        self.NT = int(total_nodes)
+        self.device = edge_index.device
+        self.layout = _lib.Layout()
+        _lib.check(L.ugs_workspace_layout(self.E, max(self.G, 0), self.NT, ctypes.byref(self.layout)))
+        self.ws = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
+        self.perm = None
+        self._info_host = torch.empty(8, dtype=torch.int64).pin_memory()
+        with torch.cuda.device(self.device):
+            self._segment(skip_lt_k)
+            info = self.info()
+            if info[CTR["unsorted"]] & 2:
+                raise RuntimeError("ptr must be non-decreasing")
+            if info[CTR["unsorted"]] & 1:
+                # Columns are not graph-contiguous (never the case for PyG batches): order them stably by
+                # graph id once and read them through `perm` from here on.
+                colkey = self.view("colkey")
+                self.perm = torch.sort(colkey, stable=True).indices.contiguous()
+                self._segment(skip_lt_k)
+                info = self.info()
+            self.n_general = int(info[CTR["n_general"]])
+            self.max_n_general = int(info[CTR["max_n_general"]])
+            self.n_skipped = int(info[CTR["n_skipped"]])
+            _lib.check(L.ugs_preproc_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.node_base,
+                                           self.k, _ptr(self.perm), self.n_general, _ptr(self.ws),
+                                           ctypes.byref(self.layout), _stream()))
+
+    def _segment(self, skip_lt_k):
+        _lib.check(_lib.lib().ugs_segment_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.k,
+                                                1 if skip_lt_k else 0, _ptr(self.perm), _ptr(self.ws),
+                                                ctypes.byref(self.layout), _stream()))
+
+    def info(self):
+        """counters[0..7] as a list of python ints (synchronises the current stream)."""
+        _lib.check(_lib.lib().ugs_batch_info(_ptr(self.ws), ctypes.byref(self.layout),
+                                             ctypes.c_void_p(self._info_host.data_ptr()), _stream()))
+        return [int(x) for x in self._info_host.tolist()]
+
+    # -- typed views into the workspace (parity tests read the deterministic stages through these) --
+    _VIEWS = {
+        "cstart": (torch.int64, lambda s: s.G + 2), "glist": (torch.int32, lambda s: s.G),
+        "counters": (torch.int64, lambda s: 16), "colkey": (torch.int32, lambda s: s.E),
+        "rowptr": (torch.int32, lambda s: s.NT + s.G), "order": (torch.int32, lambda s: s.NT),
+        "index_of": (torch.int32, lambda s: s.NT), "suffix_deg": (torch.int32, lambda s: s.NT),
+        "bucket_b": (torch.float64, lambda s: s.NT), "cum": (torch.float64, lambda s: s.NT),
+        "adj": (torch.int64, lambda s: s.NT), "suf": (torch.int64, lambda s: s.NT),
+        "csr_idx": (torch.int32, lambda s: 2 * s.E), "csr_col": (torch.int32, lambda s: 2 * s.E),
+    }
+
+    def view(self, name: str) -> torch.Tensor:
+        dt, nfn = self._VIEWS[name]
+        n = nfn(self)
+        off = getattr(self.layout, name)
+        nbytes = n * torch.empty(0, dtype=dt).element_size()
+        return self.ws[off:off + nbytes].view(dt)
+
+    def ginfo(self) -> dict:
+        """Per-graph records as CPU tensors: Z, nnz, level, n_eligible, last_viable, mult, cls."""
+        raw = self.ws[self.layout.ginfo:self.layout.ginfo + 32 * self.G].cpu()
+        z = raw.view(torch.float64).view(self.G, 4)[:, 0].clone()
+        ints = raw.view(torch.int32).view(self.G, 8)
+        return dict(Z=z, nnz=ints[:, 2].clone(), level=ints[:, 3].clone(), n_eligible=ints[:, 4].clone(),
+                    last_viable=ints[:, 5].clone(), mult=ints[:, 6].clone(), cls=ints[:, 7].clone())
+
+    # ------------------------------------------------------------------------------------------------
+    def sample(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
+               graph_index_base: int = 0, variant: str = "ref", emit: bool = True):
+        """Returns device tensors (nodes[G*m,k], edge_index[2,Ebar], edge_ptr[G*m+1], sample_ptr[G+1],
+        edge_src[Ebar]) and the stats dict. One host sync (reading Ebar) between sampling and emission."""
+        L = _lib.lib()
+        if mode not in MODES:
+            raise RuntimeError("mode must be one of: 'sample', 'graph', 'global'")
+        k = self.k if k is None else int(k)
+        m = int(m)
+        G = max(self.G, 0)
+        dev = self.device
+        with torch.cuda.device(dev):
+            nodes = torch.empty((G * m, k), dtype=torch.int64, device=dev)
+            edge_ptr = torch.empty(G * m + 1, dtype=torch.int64, device=dev)
+            sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+            sbytes = int(L.ugs_sample_scratch_bytes(G, m))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.ugs_sample_batch(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
+                                          graph_index_base, VARIANTS[variant], self.n_general, self.max_n_general,
+                                          _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch), sbytes,
+                                          _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
+            info = self.info()
+            total = info[CTR["total_edges"]]
+            stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
+                         n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
+                         n_general_graphs=self.n_general)
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            if emit:
+                _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], self.n_general,
+                                            _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr),
+                                            total, _ptr(edge_index), _ptr(edge_src), _stream()))
+        return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
+
+    def extract(self, nodes: torch.Tensor, m: int, k: int | None = None, mode: str = "sample"):
+        """Induced-edge extraction (A.7) for caller-provided node rows [G*m,k] (batch-global ids, -1 pad)."""
+        L = _lib.lib()
+        k = self.k if k is None else int(k)
+        G = max(self.G, 0)
+        dev = self.device
+        nodes = nodes.to(dev).contiguous()
+        with torch.cuda.device(dev):
+            edge_ptr = torch.empty(G * m + 1, dtype=torch.int64, device=dev)
+            sbytes = int(L.ugs_sample_scratch_bytes(G, m))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.ugs_count_edges(_ptr(self.ptr), G, self.node_base, m, k, self.n_general, _ptr(self.ws),
+                                         ctypes.byref(self.layout), _ptr(scratch), sbytes, _ptr(nodes),
+                                         _ptr(edge_ptr), _stream()))
+            total = self.info()[CTR["total_edges"]]
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], self.n_general,
+                                        _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr),
+                                        total, _ptr(edge_index), _ptr(edge_src), _stream()))
+        return edge_index, edge_ptr, edge_src
+
+
+def sample_batch_device(edge_index, ptr, m_per_graph, k, mode="sample", seed=42, node_base=0, total_nodes=None,
+                        graph_index_base=0, variant="ref"):
+    """One-shot device path: inputs and outputs are CUDA tensors. total_nodes = ptr[-1]-ptr[0] (host int)."""
+    if total_nodes is None:
+        pb = ptr[[0, -1]].tolist() if ptr.numel() > 0 else [0, 0]
+        node_base, total_nodes = pb[0], pb[1] - pb[0]
+    b = DeviceBatch(edge_index, ptr, k, node_base, total_nodes)
+    return b.sample(m_per_graph, k, mode, seed, graph_index_base, variant)

@@ -1,0 +1,156 @@
+"""ugs_sampler -- B200-native drop-in for SS-GNN's pybind11 module of the same name.
+
+Same functions, argument names, defaults, output layout and error behaviour as the reference module
+(src/samplers/ugs_sampler/src/extension.cpp:4-14, stubs __init__.pyi:1-56), so that
+`import ugs_sampler; ugs_sampler.sample_batch(edge_index, ptr, m, k, mode="sample", seed=...)`
+(gps/experiment.py:169-172,882-883) works unchanged once this directory's parent is on sys.path.
+
+Everything is computed by hand-written sm_100a kernels behind libugs_b200.so (include/ugs_b200.h).
+There is no CPU fallback: without the library or a CUDA device the calls raise RuntimeError.
+
+Differences from the reference, all deliberate:
+  * sample VALUES come from Philox4x32-10 keyed (seed, graph, sample) instead of an xorshift stream keyed on the
+    sample index only; the output LAW (A.5-A.6) is the reference's;
+  * no LRU preproc cache (the reference's key ignores k); preprocessing is recomputed per call on the GPU;
+  * CUDA input tensors are accepted (outputs then stay on the device). With CPU inputs the outputs are CPU
+    pinned int64 tensors exactly like the reference's (sampler.cpp:190); set UGS_B200_OUTPUT=cuda to keep
+    them on the GPU.
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import torch
+
+from ugs_b200 import engine as _engine
+
+__version__ = "2.2.1+b200"
+
+_registry = {}
+_registry_lock = threading.Lock()
+_next_handle = 1
+
+_EDGE_MODES = {"local": "sample", "flat": "graph", "global": "global"}
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("ugs_sampler (B200): no CUDA device available and there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _check_inputs(edge_index, ptr=None, allow_cuda=True):
+    if not isinstance(edge_index, torch.Tensor):
+        raise TypeError("edge_index must be a torch.Tensor")
+    if not allow_cuda and edge_index.is_cuda:
+        raise RuntimeError("edge_index must be on CPU")
+    if edge_index.dtype != torch.int64:
+        raise RuntimeError("edge_index must be int64")
+    if ptr is not None:
+        if ptr.dtype != torch.int64:
+            raise RuntimeError("ptr must be int64")
+
+
+def _to_host(tensors):
+    out = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        out.append(h)
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+def _want_cuda_out(inp):
+    return inp.is_cuda or os.environ.get("UGS_B200_OUTPUT", "").lower() == "cuda"
+
+
+def create_preproc(edge_index: torch.Tensor, num_nodes: int, k: int) -> int:
+    """Create preprocessing for a graph and return a handle (int). Reference: preproc.cpp:262-284."""
+    global _next_handle
+    _check_inputs(edge_index)
+    dev = edge_index.device if edge_index.is_cuda else _device()
+    n = int(num_nodes)
+    ei = edge_index.to(dev, non_blocking=True)
+    ptr = torch.tensor([0, max(n, 0)], dtype=torch.int64).to(dev, non_blocking=True)
+    b = _engine.DeviceBatch(ei, ptr, int(k), 0, max(n, 0), skip_lt_k=False)
+    b._cuda_out = _want_cuda_out(edge_index)
+    with _registry_lock:
+        h = _next_handle
+        _next_handle += 1
+        _registry[h] = b
+    return h
+
+
+def destroy_preproc(handle: int) -> None:
+    """Destroy a preprocessing handle (unknown handles are ignored, preproc.cpp:286-292)."""
+    with _registry_lock:
+        _registry.pop(int(handle), None)
+
+
+def has_graphlets(handle: int) -> bool:
+    """True if the preprocessed graph contains k-graphlets, i.e. Z > 0 (preproc.cpp:294-299)."""
+    with _registry_lock:
+        b = _registry.get(int(handle))
+    if b is None or b.G < 1:
+        return False
+    return bool(float(b.ginfo()["Z"][0]) > 0.0)
+
+
+def get_preproc_info(handle: int) -> dict:
+    """Small metadata dict (preproc.cpp:301-314); empty for an unknown handle."""
+    with _registry_lock:
+        b = _registry.get(int(handle))
+    if b is None:
+        return {}
+    gi = b.ginfo()
+    nz = int((b.view("bucket_b") > 0).sum().item())
+    return {"num_nodes": b.NT, "num_edges_stored": int(gi["nnz"][0]), "Z": float(gi["Z"][0]),
+            "bucket_count_nonzero": nz}
+
+
+def sample(handle: int, m_per_graph: int, k: int, edge_mode: str = "local", base_offset: int = 0, seed: int = 42):
+    """Sample m_per_graph subgraphs of size k from a preprocessed graph; edge_mode in {'local','flat','global'}.
+
+    Returns (nodes[m,k], edge_index[2,E], edge_ptr[m+1], edge_src[E]) like sampler.cpp:91-290."""
+    with _registry_lock:
+        b = _registry.get(int(handle))
+    if b is None:
+        raise RuntimeError("Invalid preproc handle")
+    if b.NT <= 0:
+        raise RuntimeError("No viable roots available")
+    # Any edge_mode other than 'local'/'flat' behaves as 'global' in the reference (sampler.cpp:262-273).
+    mode = _EDGE_MODES.get(edge_mode, "global")
+    (nodes, ei, eptr, _sptr, esrc), _ = b.sample(int(m_per_graph), int(k), mode, int(seed))
+    if mode == "global" and base_offset:
+        nodes = torch.where(nodes >= 0, nodes + int(base_offset), nodes)
+        ei = ei + int(base_offset)
+    outs = [nodes, ei, eptr, esrc]
+    return tuple(outs if b._cuda_out else _to_host(outs))
+
+
+def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, k: int, mode: str = "sample",
+                 seed: int = 42):
+    """Sample m_per_graph k-subgraphs per graph from a batched PyG edge_index + ptr.
+
+    Returns (nodes[G*m,k], edge_index[2,Ebar], edge_ptr[G*m+1], sample_ptr[G+1], edge_src_global[Ebar]),
+    reference ugs_sampler_batch_extension.cpp:77-300."""
+    _check_inputs(edge_index, ptr)
+    if mode not in ("sample", "graph", "global"):
+        raise RuntimeError("mode must be one of: 'sample', 'graph', 'global'")
+    dev = edge_index.device if edge_index.is_cuda else _device()
+    if ptr.is_cuda:
+        pb = ptr[[0, -1]].tolist() if ptr.numel() > 1 else [0, 0]
+    else:
+        pb = [int(ptr[0]), int(ptr[-1])] if ptr.numel() > 1 else [0, 0]
+    with torch.cuda.device(dev):
+        ei = edge_index.to(dev, non_blocking=True)
+        p = ptr.to(dev, non_blocking=True)
+        b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0])
+        outs, _stats = b.sample(int(m_per_graph), int(k), mode, int(seed))
+        sample_batch.last_stats = _stats
+        return tuple(outs if _want_cuda_out(edge_index) else _to_host(outs))
+
+
+sample_batch.last_stats = None

