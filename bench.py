@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- sampled k-graphlets/s of the UGS hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zinc|proteins|mutag|qm9|powerlaw]
+                    [--graphs G] [--impl reference]
+
+A "step" is one pass of the whole hot path over one synthetic batch resident in HBM:
+segment -> preprocess -> sample -> scan -> emit (what ugs_sampler.sample_batch does per mini-batch).
+Default workload: BASELINE.json configs[3] (ZINC/molpcba-shaped, k=8, m=64, "1M graphs sharded by graph over
+8xB200"): every rank samples its own shard of 131072 graphs (weak scaling; 8 ranks = the 1M-graph batch).
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definitions of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "ss-gnn_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "sampled k-graphlets/sec"
+UNIT = "graphlets/s"
+DEFAULT_G = {"zinc": 131072, "proteins": 1113, "mutag": 188, "qm9": 131072, "powerlaw": 1}
+KM = {"zinc": (8, 64), "proteins": (6, 100), "mutag": (6, 64), "qm9": (5, 10), "powerlaw": (6, 100000)}
+
+
+def make_workload(name: str, G: int, seed: int):
+    from ugs_b200 import synth
+    if name == "powerlaw":
+        return synth.barabasi_albert(30000, 3, seed)
+    return synth.make_batch(name, G, seed)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nme, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU sampler (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """Sample a contiguous shard of graphs with the unmodified reference, in DataLoader-sized chunks."""
+    ei, ptr, m, k, seed, chunk, use_port = args
+    import torch
+    torch.set_num_threads(1)
+    if use_port:
+        from oracle import ugs_oracle as uo
+        fn = lambda e, p: uo.sample_batch(e, p, m, k, "sample", seed)  # noqa: E731
+    else:
+        from oracle import ref_loader
+        mod = ref_loader.load("ugs_sampler", "nopin")  # pageable outputs: no CUDA context per worker
+        fn = lambda e, p: mod.sample_batch(torch.from_numpy(e), torch.from_numpy(p), m, k, "sample", seed)  # noqa: E731
+    G = len(ptr) - 1
+    done = 0
+    t0 = time.perf_counter()
+    col_graph = np.searchsorted(ptr, ei[0], side="right") - 1
+    cstart = np.searchsorted(col_graph, np.arange(G + 1))
+    for g0 in range(0, G, chunk):
+        g1 = min(G, g0 + chunk)
+        e = np.ascontiguousarray(ei[:, cstart[g0]:cstart[g1]] - ptr[g0])
+        p = np.ascontiguousarray(ptr[g0:g1 + 1] - ptr[g0])
+        fn(e, p)
+        done += (g1 - g0) * m
+    return done, time.perf_counter() - t0
+
+
+def cpu_reference_throughput(ei, ptr, m, k, seed, n_graphs, procs, chunk=256):
+    """graphlets/s of the reference CPU sampler over the first n_graphs graphs using `procs` processes."""
+    import multiprocessing as mp
+    from oracle import ref_loader
+    use_port = not ref_loader.available("ugs_sampler", "nopin")
+    G = min(n_graphs, len(ptr) - 1)
+    col_graph = np.searchsorted(ptr, ei[0], side="right") - 1
+    cstart = np.searchsorted(col_graph, np.arange(len(ptr)))
+    procs = max(1, min(procs, G))
+    bounds = np.linspace(0, G, procs + 1).astype(int)
+    jobs = []
+    for r in range(procs):
+        g0, g1 = int(bounds[r]), int(bounds[r + 1])
+        if g1 <= g0:
+            continue
+        e = np.ascontiguousarray(ei[:, cstart[g0]:cstart[g1]] - ptr[g0])
+        p = np.ascontiguousarray(ptr[g0:g1 + 1] - ptr[g0])
+        jobs.append((e, p, m, k, seed, chunk, use_port))
+    t0 = time.perf_counter()
+    if len(jobs) == 1:
+        res = [_ref_worker(jobs[0])]
+    else:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(len(jobs)) as pool:
+            # warm the pool (imports, library load) outside the timed region
+            pool.map(_ref_worker, [(j[0][:, :0], np.zeros(1, np.int64), m, k, seed, chunk, use_port) for j in jobs])
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    return {"value": total / wall, "unit": UNIT, "cores": len(jobs), "kind": "port" if use_port else "reference",
+            "sample": f"reference ugs_sampler.sample_batch (oracle/_ref, outputs pageable instead of pinned), "
+                      f"first {G} graphs of the workload, {chunk} graphs per call, cold LRU cache, "
+                      f"{len(jobs)} worker processes x 1 thread, wall {wall:.2f}s"}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    k, m = KM[args.workload]
+    procs = os.cpu_count() or 1
+    G = args.graphs or DEFAULT_G[args.workload]
+    n_sample = min(G, max(8192, procs * 2048))
+    ei, ptr = make_workload(args.workload, n_sample, 1234)
+    vals = []
+    last = None
+    for it in range(args.warmup + args.steps):
+        last = cpu_reference_throughput(ei, ptr, m, k, 42 + it, n_sample, procs)
+        if it >= args.warmup:
+            vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n_sample * m / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-shaped, k={k}, m={m}", "graphs_per_step": n_sample},
+        "cpu_baseline": dict(last, value=v),
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="zinc", choices=sorted(KM))
+    ap.add_argument("--graphs", type=int, default=0, help="graphs per rank (default: workload-specific)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ugs_b200 import _lib
+    from ugs_b200.engine import DeviceBatch
+    import ugs_sampler  # the drop-in public API (e2e leg)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 sampler has no CPU fallback")
+    L = _lib.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    k, m = KM[args.workload]
+    G = args.graphs or DEFAULT_G[args.workload]
+    ei_np, ptr_np = make_workload(args.workload, G, 1234 + rank)
+    G = len(ptr_np) - 1
+    E = ei_np.shape[1]
+    NT = int(ptr_np[-1] - ptr_np[0])
+    d_ei = torch.from_numpy(ei_np).to(dev)
+    d_ptr = torch.from_numpy(ptr_np).to(dev)
+    gbase = rank * G  # Philox is keyed on the global graph index: results do not depend on the sharding
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    stage_ms = {"preproc": [], "sample": [], "emit": []}
+    last = {}
+
+    def step(seed, timed):
+        """One pass of the hot path; returns device-event milliseconds of the whole pass."""
+        flush_buf.zero_()  # L2 flush between iterations (not timed)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        b = DeviceBatch(d_ei, d_ptr, k, int(ptr_np[0]), NT)
+        e1.record()
+        outs, stats = b.sample(m, k, "sample", seed=seed, graph_index_base=gbase, emit=False)
+        e2.record()
+        nodes, eidx, eptr, sptr, esrc = outs
+        total = stats["n_edge_entries"]
+        _lib.check(L.ugs_emit_edges(d_ptr.data_ptr(), G, int(ptr_np[0]), m, k, 0, b.n_general, b.ws.data_ptr(),
+                                    __import__("ctypes").byref(b.layout), nodes.data_ptr(), eptr.data_ptr(), total,
+                                    eidx.data_ptr(), esrc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        e3.record()
+        e3.synchronize()
+        if timed:
+            stage_ms["preproc"].append(e0.elapsed_time(e1))
+            stage_ms["sample"].append(e1.elapsed_time(e2))
+            stage_ms["emit"].append(e2.elapsed_time(e3))
+        last.update(stats=stats, total=total, n_general=b.n_general)
+        return e0.elapsed_time(e3)
+
+    for w in range(args.warmup):
+        step(100 + w, False)
+    launches0 = int(L.ugs_launch_count())
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        times = [step(1000 + s, True) for s in range(args.steps)]
+        barrier()
+    launches = int(L.ugs_launch_count()) - launches0
+    t_local = sum(times) / 1e3
+    t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max = float(t.item())
+
+    # the one collective of the design: all-gather of per-rank counts/statistics (never on the sampling path)
+    st = last["stats"]
+    svec = torch.tensor([st["n_graphlets"], st["n_edge_entries"], st["n_incomplete"], st["n_relaxed_graphs"],
+                         st["n_skipped_graphs"], st["n_general_graphs"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        gathered = [torch.empty_like(svec) for _ in range(world)]
+        dist.all_gather(gathered, svec)
+        allstats = torch.stack(gathered).sum(0).tolist()
+    else:
+        allstats = svec.tolist()
+    graphlets_step_all = allstats[0]
+    value = graphlets_step_all * args.steps / t_max
+
+    # ---- roofline: algorithmic bytes -----------------------------------------------
+    peak, peak_src = peaks()
+    ebar = st["n_edge_entries"] / max(st["n_graphlets"], 1)
+    b_alg = 8 * k + 8 + 24 * ebar + (16 * E / max(G, 1) + 16) / m          # bytes per graphlet, whole path
+    emit_bytes = 24.0 * st["n_edge_entries"]                                # the emit kernel's share per launch
+    emit_ms = sum(stage_ms["emit"]) / len(stage_ms["emit"])
+    achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
+    step_ms_local = sum(times) / len(times)
+    step_achieved = b_alg * st["n_graphlets"] / (step_ms_local * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload)
+        except Exception:
+            traffic = None
+
+    # ---- e2e: the drop-in public API with HOST buffers (H2D + D2H inside the timed region) ----------------
+    e2e = None
+    if not args.no_e2e:
+        h_ei = torch.from_numpy(ei_np).pin_memory()
+        h_ptr = torch.from_numpy(ptr_np).pin_memory()
+        d2h = 0
+        for w in range(2):
+            outs = ugs_sampler.sample_batch(h_ei, h_ptr, m, k, mode="sample", seed=7 + w)
+        barrier()
+        tt = []
+        for s in range(args.e2e_steps):
+            a, bq = ev(), ev()
+            a.record()
+            outs = ugs_sampler.sample_batch(h_ei, h_ptr, m, k, mode="sample", seed=50 + s)
+            bq.record()
+            bq.synchronize()
+            tt.append(a.elapsed_time(bq))
+            d2h = sum(o.numel() * o.element_size() for o in outs)
+            assert not outs[0].is_cuda
+        barrier()
+        te = torch.tensor([sum(tt) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": graphlets_step_all * args.e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_ei.numel() * 8 + h_ptr.numel() * 8), "d2h_bytes_per_step": int(d2h),
+               "steps": args.e2e_steps, "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu tensors"}
+        del outs
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = os.cpu_count() or 1
+        n_sample = min(G, max(8192, procs * 2048))
+        try:
+            cpu_base = cpu_reference_throughput(ei_np, ptr_np, m, k, 42, n_sample, procs)
+        except Exception as ex:  # the baseline is a report, never the product
+            cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}-shaped batch (BASELINE configs[3]: 1M graphs k=8 m=64 sharded by graph "
+                            f"over 8 GPUs -> {G} graphs per rank)" if args.workload == "zinc"
+                            else f"{args.workload}-shaped batch",
+                "k": k, "m": m, "graphs_per_rank": G, "nodes_per_rank": NT, "edge_columns_per_rank": E,
+                "mean_edge_entries_per_graphlet": ebar, "l2": "512 MiB flush between timed iterations",
+                "sharding": f"dp{world} by graph, no data-path collective",
+            },
+            "stage_ms": {kk: sum(v) / len(v) for kk, v in stage_ms.items()},
+            "roofline": {"bound": "hbm", "kernel": "k_emit_small (induced-edge emission + compaction)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms},
+            "roofline_step": {"bytes_per_graphlet": b_alg, "achieved": step_achieved, "peak": peak, "unit": "GB/s",
+                              "frac": step_achieved / peak},
+            "cpu_baseline": cpu_base,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "stats_all_ranks": dict(zip(["n_graphlets", "n_edge_entries", "n_incomplete", "n_relaxed_graphs",
+                                         "n_skipped_graphs", "n_general_graphs"], allstats)),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,8 @@ typedef struct ugs_ginfo {
 #define UGS_CTR_SCAN_TICKET 8
 
 int ugs_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic; for measurement). */
+uint64_t ugs_launch_count(void);
 const char* ugs_last_error(void);
 
 /* Sizes and offsets of the workspace for a batch with E columns, G graphs and NT = ptr[G]-ptr[0] nodes. */

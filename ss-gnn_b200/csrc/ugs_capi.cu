@@ -15,3 +15,6 @@ int ugs_set_error(int code, const char* fmt, ...) {
 
 extern "C" const char* ugs_last_error(void) { return g_err; }
 extern "C" int ugs_abi_version(void) { return UGS_B200_ABI_VERSION; }
+
+unsigned long long g_ugs_launches = 0;
+extern "C" uint64_t ugs_launch_count(void) { return g_ugs_launches; }

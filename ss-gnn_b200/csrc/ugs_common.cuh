@@ -19,11 +19,13 @@ int ugs_set_error(int code, const char* fmt, ...);
         if (_e != cudaSuccess)                                                           \
             return ugs_set_error(UGS_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
+extern unsigned long long g_ugs_launches;  // kernels launched by this library (bench.py reports it)
 #define UGS_LAUNCH_CHECK(name)                                                           \
     do {                                                                                 \
         cudaError_t _e = cudaGetLastError();                                             \
         if (_e != cudaSuccess)                                                           \
             return ugs_set_error(UGS_ECUDA, "launch %s failed: %s", name, cudaGetErrorString(_e)); \
+        ++g_ugs_launches;                                                                \
     } while (0)
 
 // Typed views into the workspace.

@@ -11,8 +11,7 @@
 #include "ugs_common.cuh"
 
 #define SAMP_WARPS 8
-#define EMIT_WARPS 4
-#define EMIT_STAGE 2048  // staged edge entries per warp tile (32 samples)
+#define EMIT_WARPS 8
 
 // =====================================================================================================
 // Bitmask path: sample + count
@@ -383,29 +382,22 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 }
 
 // =====================================================================================================
-// Bitmask path: emission with shared-memory staging and coalesced stores
+// Bitmask path: emission. One thread walks the CSR rows of its sample (a single flattened loop over
+// (j, p), so lanes only wait for the longest sample, not the longest row), packs every hit into a 32-bit
+// staging word in shared memory at the sample's final offset, and the warp then flushes the staged run
+// with fully coalesced 8-byte stores (32 consecutive output entries per store instruction).
 // =====================================================================================================
+#define EMIT_STAGE 1280  // staged entries per flush; a sample never has more than 768 (= 2 * max columns)
+
 struct __align__(16) SmallEmit {
-    u32 stage[EMIT_STAGE];
-    i32 col[2 * UGS_SMALL_MAX_COLS];
-    unsigned char tile[32][16];
-    unsigned short rowptr[66];
+    u32 stage[EMIT_STAGE];            // csr position p << 15 | sample lane << 10 | l << 5 | j
+    u32 rowrange[64];                 // rowptr[v] | rowptr[v+1] << 16
+    unsigned char tile[32][16];       // node rows as local ids, 0xFF = -1
+    unsigned char lmap[32][64];       // local vertex id -> position j inside its sample
     unsigned char idx[2 * UGS_SMALL_MAX_COLS];
 };
 
-__device__ __forceinline__ int find_local(u64 nlo, u64 nhi, int x) {
-    const u32 pat = (u32)x * 0x01010101u;
-    u32 m0 = __vcmpeq4((u32)nlo, pat);
-    if (m0) return (__ffs(m0) - 1) >> 3;
-    m0 = __vcmpeq4((u32)(nlo >> 32), pat);
-    if (m0) return 4 + ((__ffs(m0) - 1) >> 3);
-    m0 = __vcmpeq4((u32)nhi, pat);
-    if (m0) return 8 + ((__ffs(m0) - 1) >> 3);
-    m0 = __vcmpeq4((u32)(nhi >> 32), pat);
-    return 12 + ((__ffs(m0) - 1) >> 3);
-}
-
-__global__ void __launch_bounds__(EMIT_WARPS * 32)
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, WS w, const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr,
              i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
@@ -424,20 +416,17 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
     const i64 lo = ptr[g];
     const int n = (int)(ptr[g + 1] - lo);
     const i64 nb = lo - node_base;
-    // nothing to do if this item's samples emit no entries
-    {
+    {   // nothing to do if this item's samples emit no entries
         const i64 sA = g * m + (i64)t0 * 32, sB = min(g * m + m, g * m + (i64)t1 * 32);
         if (edge_ptr[sA] == edge_ptr[sB]) return;
     }
     SmallEmit& s = sm_all[warp];
+    const i32* __restrict__ gcol = w.csr_col + 2 * w.cstart[g];
     {
         const u32* rp = w.rowptr + nb + g;
-        const i64 cb = 2 * w.cstart[g];
-        for (int v = lane; v <= n; v += 32) s.rowptr[v] = (unsigned short)rp[v];
-        for (int p = lane; p < gi.nnz; p += 32) {
-            s.idx[p] = (unsigned char)w.csr_idx[cb + p];
-            s.col[p] = w.csr_col[cb + p];
-        }
+        const i32* ci = w.csr_idx + 2 * w.cstart[g];
+        for (int v = lane; v < n; v += 32) s.rowrange[v] = rp[v] | (rp[v + 1] << 16);
+        for (int p = lane; p < gi.nnz; p += 32) s.idx[p] = (unsigned char)ci[p];
     }
     const int r32 = 32 % k, q32 = 32 / k;
 
@@ -445,8 +434,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 s0 = g * m + (i64)t * 32;
         const int nv = (int)min((i64)32, m - (i64)t * 32);
         __syncwarp();
-        // node rows -> shared tile (coalesced read)
-        {
+        {   // node rows -> shared tile (coalesced read)
             int sidx = lane / k, j = lane - sidx * k;
             const i64* in = nodes + s0 * k;
             for (int e = lane; e < nv * k; e += 32) {
@@ -458,66 +446,85 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         }
         const i64 my_lo = (lane < nv) ? edge_ptr[s0 + lane] : 0;
         const i64 tile_end = edge_ptr[s0 + nv];
-        const i64 tile_base = __shfl_sync(FULL_MASK, my_lo, 0);
-        const int tile_total = (int)min(tile_end - tile_base, (i64)0x7fffffff);
+        const i64 my_hi = __shfl_down_sync(FULL_MASK, my_lo, 1);
+        const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
         __syncwarp();
-        if (tile_total == 0) continue;
-        const bool staged = tile_total <= EMIT_STAGE;
+        if (tile_end == __shfl_sync(FULL_MASK, my_lo, 0)) continue;
+        // per-sample prep by the owning lane: member mask + local-index map
+        u64 nlo = ~0ull, nhi = ~0ull, S = 0;
         if (lane < nv) {
             const ulonglong2 nn = *reinterpret_cast<const ulonglong2*>(&s.tile[lane][0]);
-            const u64 nlo = nn.x, nhi = nn.y;
-            u64 S = 0;
+            nlo = nn.x; nhi = nn.y;
             bool complete = true;
             for (int j = 0; j < k; ++j) {
                 const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                if (v == 0xFF) complete = false; else S |= 1ull << v;
+                if (v == 0xFF) complete = false; else { S |= 1ull << v; s.lmap[lane][v] = (unsigned char)j; }
             }
-            if (complete) {  // incomplete rows emit nothing (sampler.cpp:220-223)
-                i64 off = my_lo - tile_base;
-                const i64 i_in_graph = (i64)t * 32 + lane;
-                for (int j = 0; j < k; ++j) {
-                    const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                    const int pe = s.rowptr[v + 1];
-                    for (int p = s.rowptr[v]; p < pe; ++p) {
-                        const int x = s.idx[p];
-                        if ((S >> x) & 1ull) {
-                            const int l = find_local(nlo, nhi, x);
-                            if (staged) {
-                                s.stage[off] = (u32)j | ((u32)l << 5) | ((u32)lane << 10) | ((u32)p << 15);
-                            } else {
-                                i64 a, b;
-                                if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
-                                else if (mode == UGS_MODE_GRAPH) { a = i_in_graph * k + j; b = i_in_graph * k + l; }
-                                else { a = lo + v; b = lo + x; }
-                                const i64 o = tile_base + off;
-                                if (o < total) { out_u[o] = a; out_v[o] = b; out_src[o] = (i64)s.col[p]; }
-                            }
-                            off++;
-                        }
-                    }
-                }
-            }
+            if (!complete || my_end == my_lo) S = 0;  // incomplete rows emit nothing (sampler.cpp:220-223)
         }
-        __syncwarp();
-        if (staged) {
-            for (int e = lane; e < tile_total; e += 32) {
-                const u32 pk = s.stage[e];
-                const int j = pk & 31, l = (pk >> 5) & 31, sl = (pk >> 10) & 31, p = pk >> 15;
-                i64 a, b;
-                if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
-                else if (mode == UGS_MODE_GRAPH) {
-                    const i64 ik = ((i64)t * 32 + sl) * k;
-                    a = ik + j; b = ik + l;
-                } else { a = lo + s.tile[sl][j]; b = lo + s.tile[sl][l]; }
-                const i64 o = tile_base + e;
-                if (o < total) {
-                    out_u[o] = a;
-                    out_v[o] = b;
-                    out_src[o] = (i64)s.col[p];
+        // sub-batches of consecutive samples whose entries fit the staging buffer
+        int sa = 0;
+        while (sa < nv) {
+            const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
+            const u32 fits = __ballot_sync(FULL_MASK, lane >= sa && lane < nv && (my_end - base) <= EMIT_STAGE);
+            // samples sa..sb-1 fit: sb = first lane >= sa that does not fit
+            const u32 nofit = ~fits & ~((1u << sa) - 1u);
+            const int sb = nofit ? min(nv, __ffs(nofit) - 1) : nv;
+            const int run = (int)(((sb == nv) ? tile_end : __shfl_sync(FULL_MASK, my_lo, sb & 31)) - base);
+            if (lane >= sa && lane < sb && S) {
+                int off = (int)(my_lo - base);
+                int j = 0;
+                int v = (int)(nlo & 0xFF);
+                u32 rr = s.rowrange[v];
+                int p = rr & 0xFFFF, pe = rr >> 16;
+                while (true) {
+                    if (p == pe) {
+                        if (++j == k) break;
+                        v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                        rr = s.rowrange[v];
+                        p = rr & 0xFFFF; pe = rr >> 16;
+                        continue;
+                    }
+                    const int x = s.idx[p];
+                    if ((S >> x) & 1ull) {
+                        s.stage[off] = ((u32)p << 15) | ((u32)lane << 10) | ((u32)s.lmap[lane][x] << 5) | (u32)j;
+                        off++;
+                    }
+                    p++;
                 }
             }
+            __syncwarp();
+            // ---- flush: entry e of the run goes to global position base + e ------------------------------
+            if (mode == UGS_MODE_SAMPLE) {
+                for (int e = lane; e < run; e += 32) {
+                    const u32 pk = s.stage[e];
+                    const i64 o = base + e;
+                    out_u[o] = (i64)(pk & 31u);
+                    out_v[o] = (i64)((pk >> 5) & 31u);
+                    out_src[o] = (i64)__ldg(gcol + (pk >> 15));
+                }
+            } else {
+                for (int e = lane; e < run; e += 32) {
+                    const u32 pk = s.stage[e];
+                    const i64 o = base + e;
+                    const int j = pk & 31, l = (pk >> 5) & 31, sl = (pk >> 10) & 31;
+                    i64 av, bv;
+                    if (mode == UGS_MODE_GRAPH) {
+                        const i64 ik = ((i64)t * 32 + sl) * k;
+                        av = ik + j; bv = ik + l;
+                    } else {
+                        av = lo + s.tile[sl][j]; bv = lo + s.tile[sl][l];
+                    }
+                    out_u[o] = av;
+                    out_v[o] = bv;
+                    out_src[o] = (i64)__ldg(gcol + (pk >> 15));
+                }
+            }
+            __syncwarp();
+            sa = sb;
         }
     }
+    (void)total;
 }
 
 // =====================================================================================================

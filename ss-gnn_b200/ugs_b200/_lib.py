@@ -14,7 +14,7 @@ SOURCES = ["ugs_preproc.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
-    "ugs_abi_version", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
+    "ugs_abi_version", "ugs_launch_count", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
     "ugs_preproc_batch", "ugs_sample_scratch_bytes", "ugs_sample_batch", "ugs_emit_edges", "ugs_count_edges",
 ]
 
@@ -62,6 +62,7 @@ def lib():
     LP = ctypes.POINTER(Layout)
     L.ugs_abi_version.restype = ci
     L.ugs_last_error.restype = ctypes.c_char_p
+    L.ugs_launch_count.restype = ctypes.c_uint64
     L.ugs_workspace_layout.argtypes = [i64, i64, i64, LP]
     L.ugs_segment_batch.argtypes = [vp, i64, vp, i64, ci, ci, vp, vp, LP, vp]
     L.ugs_batch_info.argtypes = [vp, LP, vp, vp]
@@ -71,8 +72,6 @@ def lib():
     L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
-    for name in dir(L):
-        pass
     _LIB = L
     return L
 
