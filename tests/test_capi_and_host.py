@@ -1,0 +1,110 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ugs_b200.h declares; host-only entry points
+work without a GPU; the drop-in modules keep the reference's signatures and fail loudly without CUDA."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "ugs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ugs_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ugs_b200 import _lib
+    so = _lib.build()
+    L = ctypes.CDLL(so)
+    names = _declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ugs_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= set(names)
+    assert L.ugs_abi_version() == 1
+
+
+def test_workspace_layout_is_host_only_and_consistent():
+    from ugs_b200 import _lib
+    L = _lib.lib()
+    lay = _lib.Layout()
+    _lib.check(L.ugs_workspace_layout(1000, 10, 300, ctypes.byref(lay)))
+    offs = [getattr(lay, f) for f, _ in _lib.Layout._fields_[1:]]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert lay.total_bytes > offs[-1]
+    assert lay.csr_col - lay.csr_idx >= 4 * 2 * 1000
+    with pytest.raises(RuntimeError, match="too large"):
+        _lib.check(L.ugs_workspace_layout(1 << 31, 10, 300, ctypes.byref(lay)))
+    assert L.ugs_sample_scratch_bytes(10, 64) >= 16
+
+
+def test_dropin_signatures_match_the_reference_stubs():
+    """Argument names/defaults are part of the ABI (keyword callers: gps/utils/wl_vocab.py:144-151)."""
+    import ugs_sampler as us
+    sig = inspect.signature(us.sample_batch)
+    assert list(sig.parameters) == ["edge_index", "ptr", "m_per_graph", "k", "mode", "seed"]
+    assert sig.parameters["mode"].default == "sample" and sig.parameters["seed"].default == 42
+    sig = inspect.signature(us.sample)
+    assert list(sig.parameters) == ["handle", "m_per_graph", "k", "edge_mode", "base_offset", "seed"]
+    assert sig.parameters["edge_mode"].default == "local" and sig.parameters["base_offset"].default == 0
+    assert list(inspect.signature(us.create_preproc).parameters) == ["edge_index", "num_nodes", "k"]
+    for f in ("destroy_preproc", "has_graphlets", "get_preproc_info"):
+        assert list(inspect.signature(getattr(us, f)).parameters) == ["handle"]
+    assert us.get_preproc_info(12345) == {} and us.has_graphlets(12345) is False
+    us.destroy_preproc(12345)  # unknown handles are ignored
+    with pytest.raises(RuntimeError, match="Invalid preproc handle"):
+        us.sample(12345, 1, 3)
+
+
+def test_dropin_argument_errors_and_no_cpu_fallback():
+    import torch
+    import ugs_sampler as us
+    ei = torch.tensor([[0, 1], [1, 2]])
+    ptr = torch.tensor([0, 3])
+    with pytest.raises(RuntimeError, match="int64"):
+        us.sample_batch(ei.to(torch.int32), ptr, 2, 2)
+    with pytest.raises(RuntimeError, match="ptr must be int64"):
+        us.sample_batch(ei, ptr.to(torch.int32), 2, 2)
+    with pytest.raises(RuntimeError, match="mode must be one of"):
+        us.sample_batch(ei, ptr, 2, 2, mode="bogus")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            us.sample_batch(ei, ptr, 2, 2)
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not import, include, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "ss-gnn_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            txt = open(os.path.join(dp, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+            assert not re.search(r"#include[^\n]*oracle", txt), f
+            assert "libugs_oracle" not in txt and "ref_loader" not in txt, f
+
+
+def test_synthetic_workloads_have_the_named_shapes():
+    from ugs_b200 import synth
+    ei, ptr = synth.make_batch("zinc", 500, seed=1)
+    n = np.diff(ptr)
+    assert n.min() >= 9 and n.max() <= 38
+    assert (ei[0] != ei[1]).all()
+    # bidirectional and graph-contiguous
+    key = set(map(tuple, ei.T.tolist()))
+    assert all((b, a) in key for a, b in key)
+    g0 = np.searchsorted(ptr, ei[0], side="right") - 1
+    g1 = np.searchsorted(ptr, ei[1], side="right") - 1
+    assert (g0 == g1).all() and (np.diff(g0) >= 0).all()
+    assert 1.9 < ei.shape[1] / ptr[-1] < 2.4  # average degree ~2.15
+    ei, ptr = synth.make_batch("proteins", 400, seed=2)
+    assert np.diff(ptr).max() <= 620 and np.diff(ptr).min() >= 4
+    ei, ptr = synth.barabasi_albert(500, 3, seed=3)
+    deg = np.bincount(ei[0], minlength=500)
+    assert deg.max() > 20 and ptr.tolist() == [0, 500]
