@@ -139,9 +139,10 @@ int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m
 
 /* A.7 -- induced-edge emission for the node rows in `nodes` (normally the ones ugs_sample_batch wrote; any
  * rows whose per-sample counts are in edge_ptr work, which is how the extraction stage is pinned against the
- * reference's own samples). edge_index_out: [2,total] (row 1 at +total), edge_src_out: [total]. */
+ * reference's own samples). edge_index_out: [2,total] (row 1 at +total), edge_src_out: [total].
+ * use_perm: 1 if the workspace was built with a column permutation (ugs_segment_batch perm != NULL). */
 int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode,
-                   int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                   int use_perm, int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
                    const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
                    void* stream);
 

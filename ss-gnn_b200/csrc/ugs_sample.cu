@@ -388,19 +388,23 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 // with fully coalesced 8-byte stores (32 consecutive output entries per store instruction).
 // =====================================================================================================
 #define EMIT_STAGE 1280  // staged entries per flush; a sample never has more than 768 (= 2 * max columns)
+#define LMAP_STRIDE 68   // 17 words: the 32 per-sample rows start in 32 different banks
 
 struct __align__(16) SmallEmit {
-    u32 stage[EMIT_STAGE];            // csr position p << 15 | sample lane << 10 | l << 5 | j
-    u32 rowrange[64];                 // rowptr[v] | rowptr[v+1] << 16
-    unsigned char tile[32][16];       // node rows as local ids, 0xFF = -1
-    unsigned char lmap[32][64];       // local vertex id -> position j inside its sample
-    unsigned char idx[2 * UGS_SMALL_MAX_COLS];
+    u32 stage[EMIT_STAGE];                  // payload << 15 | sample lane << 10 | l << 5 | j
+    u32 rowrange[64];                       // rowptr[v] | rowptr[v+1] << 16
+    unsigned char tile[32][16];             // node rows as local ids, 0xFF = -1
+    unsigned char lmap[32][LMAP_STRIDE];    // local vertex id -> position inside its sample, 0xFF = not a member
+    unsigned short ent[2 * UGS_SMALL_MAX_COLS];  // CSR entry: neighbour id | payload << 6
 };
+// payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
+// when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
 
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
-             i64 items_per_graph, WS w, const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr,
-             i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
+             i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
+             const i64* __restrict__ edge_ptr, i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v,
+             i64* __restrict__ out_src) {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     SmallEmit* sm_all = reinterpret_cast<SmallEmit*>(emit_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -421,14 +425,22 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         if (edge_ptr[sA] == edge_ptr[sB]) return;
     }
     SmallEmit& s = sm_all[warp];
-    const i32* __restrict__ gcol = w.csr_col + 2 * w.cstart[g];
+    const i64 c0 = w.cstart[g];
+    const i32* __restrict__ gcol = w.csr_col + 2 * c0;
     {
         const u32* rp = w.rowptr + nb + g;
-        const i32* ci = w.csr_idx + 2 * w.cstart[g];
+        const i32* ci = w.csr_idx + 2 * c0;
         for (int v = lane; v < n; v += 32) s.rowrange[v] = rp[v] | (rp[v + 1] << 16);
-        for (int p = lane; p < gi.nnz; p += 32) s.idx[p] = (unsigned char)ci[p];
+        for (int p = lane; p < gi.nnz; p += 32) {
+            const u32 payload = use_perm ? (u32)p : (u32)(gcol[p] - (i32)c0);
+            s.ent[p] = (unsigned short)((u32)ci[p] | (payload << 6));
+        }
+        u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
+#pragma unroll
+        for (int q = 0; q < LMAP_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
     }
     const int r32 = 32 % k, q32 = 32 / k;
+    const unsigned char* lrow = &s.lmap[lane][0];
 
     for (int t = t0; t < t1; ++t) {
         const i64 s0 = g * m + (i64)t * 32;
@@ -450,66 +462,67 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
         __syncwarp();
         if (tile_end == __shfl_sync(FULL_MASK, my_lo, 0)) continue;
-        // per-sample prep by the owning lane: member mask + local-index map
-        u64 nlo = ~0ull, nhi = ~0ull, S = 0;
-        if (lane < nv) {
+        // per-sample prep by the owning lane: local-index map (doubles as the membership test)
+        u64 nlo = ~0ull, nhi = ~0ull;
+        bool walk = false;
+        if (lane < nv && my_end > my_lo) {  // rows with a -1 have no entries (sampler.cpp:220-223)
             const ulonglong2 nn = *reinterpret_cast<const ulonglong2*>(&s.tile[lane][0]);
             nlo = nn.x; nhi = nn.y;
-            bool complete = true;
+            walk = true;
             for (int j = 0; j < k; ++j) {
                 const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                if (v == 0xFF) complete = false; else { S |= 1ull << v; s.lmap[lane][v] = (unsigned char)j; }
+                s.lmap[lane][v] = (unsigned char)j;
             }
-            if (!complete || my_end == my_lo) S = 0;  // incomplete rows emit nothing (sampler.cpp:220-223)
         }
         // sub-batches of consecutive samples whose entries fit the staging buffer
         int sa = 0;
         while (sa < nv) {
             const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
             const u32 fits = __ballot_sync(FULL_MASK, lane >= sa && lane < nv && (my_end - base) <= EMIT_STAGE);
-            // samples sa..sb-1 fit: sb = first lane >= sa that does not fit
             const u32 nofit = ~fits & ~((1u << sa) - 1u);
             const int sb = nofit ? min(nv, __ffs(nofit) - 1) : nv;
             const int run = (int)(((sb == nv) ? tile_end : __shfl_sync(FULL_MASK, my_lo, sb & 31)) - base);
-            if (lane >= sa && lane < sb && S) {
-                int off = (int)(my_lo - base);
+            if (walk && lane >= sa && lane < sb) {
+                u32* st = s.stage + (int)(my_lo - base);
+                u32 pj = (u32)lane << 10;  // | j
                 int j = 0;
-                int v = (int)(nlo & 0xFF);
-                u32 rr = s.rowrange[v];
+                u32 rr = s.rowrange[(int)(nlo & 0xFF)];
                 int p = rr & 0xFFFF, pe = rr >> 16;
                 while (true) {
                     if (p == pe) {
                         if (++j == k) break;
-                        v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
                         rr = s.rowrange[v];
                         p = rr & 0xFFFF; pe = rr >> 16;
+                        pj++;
                         continue;
                     }
-                    const int x = s.idx[p];
-                    if ((S >> x) & 1ull) {
-                        s.stage[off] = ((u32)p << 15) | ((u32)lane << 10) | ((u32)s.lmap[lane][x] << 5) | (u32)j;
-                        off++;
-                    }
+                    const u32 e = s.ent[p];
+                    const u32 l = lrow[e & 63u];
+                    if (l != 0xFFu) *st++ = ((e >> 6) << 15) | (l << 5) | pj;
                     p++;
                 }
             }
             __syncwarp();
             // ---- flush: entry e of the run goes to global position base + e ------------------------------
-            if (mode == UGS_MODE_SAMPLE) {
+            if (mode == UGS_MODE_SAMPLE && !use_perm) {
+#pragma unroll 4
                 for (int e = lane; e < run; e += 32) {
                     const u32 pk = s.stage[e];
                     const i64 o = base + e;
                     out_u[o] = (i64)(pk & 31u);
                     out_v[o] = (i64)((pk >> 5) & 31u);
-                    out_src[o] = (i64)__ldg(gcol + (pk >> 15));
+                    out_src[o] = c0 + (i64)(pk >> 15);
                 }
             } else {
+#pragma unroll 2
                 for (int e = lane; e < run; e += 32) {
                     const u32 pk = s.stage[e];
                     const i64 o = base + e;
                     const int j = pk & 31, l = (pk >> 5) & 31, sl = (pk >> 10) & 31;
                     i64 av, bv;
-                    if (mode == UGS_MODE_GRAPH) {
+                    if (mode == UGS_MODE_SAMPLE) { av = j; bv = l; }
+                    else if (mode == UGS_MODE_GRAPH) {
                         const i64 ik = ((i64)t * 32 + sl) * k;
                         av = ik + j; bv = ik + l;
                     } else {
@@ -517,11 +530,18 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                     }
                     out_u[o] = av;
                     out_v[o] = bv;
-                    out_src[o] = (i64)__ldg(gcol + (pk >> 15));
+                    out_src[o] = use_perm ? (i64)__ldg(gcol + (pk >> 15)) : c0 + (i64)(pk >> 15);
                 }
             }
             __syncwarp();
             sa = sb;
+        }
+        // un-set this tile's members so the map is all-0xFF again
+        if (walk) {
+            for (int j = 0; j < k; ++j) {
+                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                s.lmap[lane][v] = (unsigned char)0xFF;
+            }
         }
     }
     (void)total;
@@ -695,7 +715,7 @@ extern "C" int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base,
 }
 
 extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode,
-                              int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                              int use_perm, int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
                               const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
                               void* stream_) {
     if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
@@ -714,7 +734,7 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
         const size_t smem = sizeof(SmallEmit) * EMIT_WARPS;
         UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_emit_small<<<(unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS), EMIT_WARPS * 32, smem, st>>>(
-            ptr, G, node_base, m, k, mode, tpi, ipg, w, nodes, edge_ptr, total, out_u, out_v, edge_src_out);
+            ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w, nodes, edge_ptr, total, out_u, out_v, edge_src_out);
         UGS_LAUNCH_CHECK("k_emit_small");
     }
     if (n_general > 0) {

@@ -143,7 +143,7 @@ class DeviceBatch:
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
             if emit:
-                _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], self.n_general,
+                _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,
                                             _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr),
                                             total, _ptr(edge_index), _ptr(edge_src), _stream()))
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
@@ -165,7 +165,7 @@ class DeviceBatch:
             total = self.info()[CTR["total_edges"]]
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
-            _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], self.n_general,
+            _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,
                                         _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr),
                                         total, _ptr(edge_index), _ptr(edge_src), _stream()))
         return edge_index, edge_ptr, edge_src
