@@ -387,20 +387,31 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 // staging word in shared memory at the sample's final offset, and the warp then flushes the staged run
 // with fully coalesced 8-byte stores (32 consecutive output entries per store instruction).
 // =====================================================================================================
+#ifndef EMIT_STAGE
 #define EMIT_STAGE 1280  // staged entries per flush; a sample never has more than 768 (= 2 * max columns)
+#endif
+#ifndef EMIT_DIRECT_NODES
+#define EMIT_DIRECT_NODES 0
+#endif
+#ifndef EMIT_UNROLLED_FLUSH
+#define EMIT_UNROLLED_FLUSH 1
+#endif
+#ifndef EMIT_MIN_BLOCKS
+#define EMIT_MIN_BLOCKS 3
+#endif
 #define LMAP_STRIDE 68   // 17 words: the 32 per-sample rows start in 32 different banks
 
 struct __align__(16) SmallEmit {
     u32 stage[EMIT_STAGE];                  // payload << 15 | sample lane << 10 | l << 5 | j
-    u32 rowrange[64];                       // rowptr[v] | rowptr[v+1] << 16
-    unsigned char tile[32][16];             // node rows as local ids, 0xFF = -1
+    u32 rowrange[64];                       // byte offsets into ent[]: 2*rowptr[v] | 2*rowptr[v+1] << 16
+    unsigned char tile[32][16];             // node rows as local ids (mode "global" only)
     unsigned char lmap[32][LMAP_STRIDE];    // local vertex id -> position inside its sample, 0xFF = not a member
     unsigned short ent[2 * UGS_SMALL_MAX_COLS];  // CSR entry: neighbour id | payload << 6
 };
 // payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
 // when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
 
-__global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
+__global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v,
@@ -409,7 +420,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
     SmallEmit* sm_all = reinterpret_cast<SmallEmit*>(emit_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
-    const i64 g = item / items_per_graph;
+    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
     if (g >= G) return;
     const ugs_ginfo gi = w.ginfo[g];
     if (gi.cls != 1 || gi.nnz == 0) return;
@@ -430,7 +441,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
     {
         const u32* rp = w.rowptr + nb + g;
         const i32* ci = w.csr_idx + 2 * c0;
-        for (int v = lane; v < n; v += 32) s.rowrange[v] = rp[v] | (rp[v + 1] << 16);
+        for (int v = lane; v < n; v += 32) s.rowrange[v] = (rp[v] << 1) | (rp[v + 1] << 17);
         for (int p = lane; p < gi.nnz; p += 32) {
             const u32 payload = use_perm ? (u32)p : (u32)(gcol[p] - (i32)c0);
             s.ent[p] = (unsigned short)((u32)ci[p] | (payload << 6));
@@ -439,14 +450,39 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
 #pragma unroll
         for (int q = 0; q < LMAP_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
     }
-    const int r32 = 32 % k, q32 = 32 / k;
-    const unsigned char* lrow = &s.lmap[lane][0];
+    unsigned char* lrow = &s.lmap[lane][0];
+    const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent);
 
     for (int t = t0; t < t1; ++t) {
         const i64 s0 = g * m + (i64)t * 32;
         const int nv = (int)min((i64)32, m - (i64)t * 32);
         __syncwarp();
+        const i64 my_lo = (lane < nv) ? edge_ptr[s0 + lane] : 0;
+        const i64 tile_end = edge_ptr[s0 + nv];
+        const i64 my_hi = __shfl_down_sync(FULL_MASK, my_lo, 1);
+        const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
+        if (tile_end == __shfl_sync(FULL_MASK, my_lo, 0)) continue;
+        // per-sample state of the owning lane: node bytes in registers + local-index map (= membership test).
+        // Rows with a -1 have no entries (sampler.cpp:220-223), so only rows with entries are read.
+        u32 nb4[4] = {~0u, ~0u, ~0u, ~0u};
+        const bool walk = (lane < nv) && (my_end > my_lo);
+#if EMIT_DIRECT_NODES
+        if (walk) {
+            const i64* in = nodes + (s0 + lane) * k;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < k) {
+                    const u32 v = (u32)(in[j] - lo) & 0xFFu;
+                    nb4[j >> 2] = (nb4[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (v << (8 * (j & 3)));
+                    lrow[v] = (unsigned char)j;
+                }
+            }
+            if (mode == UGS_MODE_GLOBAL)
+                *reinterpret_cast<uint4*>(&s.tile[lane][0]) = make_uint4(nb4[0], nb4[1], nb4[2], nb4[3]);
+        }
+#else
         {   // node rows -> shared tile (coalesced read)
+            const int r32 = 32 % k, q32 = 32 / k;
             int sidx = lane / k, j = lane - sidx * k;
             const i64* in = nodes + s0 * k;
             for (int e = lane; e < nv * k; e += 32) {
@@ -456,63 +492,73 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                 if (j >= k) { j -= k; sidx++; }
             }
         }
-        const i64 my_lo = (lane < nv) ? edge_ptr[s0 + lane] : 0;
-        const i64 tile_end = edge_ptr[s0 + nv];
-        const i64 my_hi = __shfl_down_sync(FULL_MASK, my_lo, 1);
-        const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
         __syncwarp();
-        if (tile_end == __shfl_sync(FULL_MASK, my_lo, 0)) continue;
-        // per-sample prep by the owning lane: local-index map (doubles as the membership test)
-        u64 nlo = ~0ull, nhi = ~0ull;
-        bool walk = false;
-        if (lane < nv && my_end > my_lo) {  // rows with a -1 have no entries (sampler.cpp:220-223)
-            const ulonglong2 nn = *reinterpret_cast<const ulonglong2*>(&s.tile[lane][0]);
-            nlo = nn.x; nhi = nn.y;
-            walk = true;
-            for (int j = 0; j < k; ++j) {
-                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                s.lmap[lane][v] = (unsigned char)j;
-            }
+        if (walk) {
+            const uint4 nn = *reinterpret_cast<const uint4*>(&s.tile[lane][0]);
+            nb4[0] = nn.x; nb4[1] = nn.y; nb4[2] = nn.z; nb4[3] = nn.w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)j;
         }
+#endif
+        // balanced sub-batches: when the tile does not fit the staging buffer, aim for equal shares
+        const int tile_total = (int)min(tile_end - __shfl_sync(FULL_MASK, my_lo, 0), (i64)0x7fffffff);
+        const int nsplit = (tile_total + EMIT_STAGE - 1) / EMIT_STAGE;
+        const int cap_eff = (nsplit <= 1) ? EMIT_STAGE : min(EMIT_STAGE, tile_total / nsplit + 48);
         // sub-batches of consecutive samples whose entries fit the staging buffer
         int sa = 0;
         while (sa < nv) {
             const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
-            const u32 fits = __ballot_sync(FULL_MASK, lane >= sa && lane < nv && (my_end - base) <= EMIT_STAGE);
+            const u32 fits = __ballot_sync(FULL_MASK, lane >= sa && lane < nv && (my_end - base) <= cap_eff);
             const u32 nofit = ~fits & ~((1u << sa) - 1u);
-            const int sb = nofit ? min(nv, __ffs(nofit) - 1) : nv;
+            int sb = nofit ? min(nv, __ffs(nofit) - 1) : nv;
+            if (sb == sa) sb = sa + 1;  // a single sample always fits EMIT_STAGE (<= 768 entries)
             const int run = (int)(((sb == nv) ? tile_end : __shfl_sync(FULL_MASK, my_lo, sb & 31)) - base);
             if (walk && lane >= sa && lane < sb) {
                 u32* st = s.stage + (int)(my_lo - base);
                 u32 pj = (u32)lane << 10;  // | j
                 int j = 0;
-                u32 rr = s.rowrange[(int)(nlo & 0xFF)];
-                int p = rr & 0xFFFF, pe = rr >> 16;
+                u32 rr = s.rowrange[nb4[0] & 0xFFu];
+                u32 p = rr & 0xFFFFu, pe = rr >> 16;  // byte offsets into ent[]
                 while (true) {
                     if (p == pe) {
                         if (++j == k) break;
-                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                        const u32 wsel = (j < 4) ? nb4[0] : (j < 8) ? nb4[1] : (j < 12) ? nb4[2] : nb4[3];
+                        const u32 v = (wsel >> (8 * (j & 3))) & 0xFFu;
                         rr = s.rowrange[v];
-                        p = rr & 0xFFFF; pe = rr >> 16;
+                        p = rr & 0xFFFFu; pe = rr >> 16;
                         pj++;
                         continue;
                     }
-                    const u32 e = s.ent[p];
+                    const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
                     const u32 l = lrow[e & 63u];
-                    if (l != 0xFFu) *st++ = ((e >> 6) << 15) | (l << 5) | pj;
-                    p++;
+                    if (l != 0xFFu) *st++ = ((e & 0xFFC0u) << 9) + (l << 5) + pj;
+                    p += 2;
                 }
             }
             __syncwarp();
             // ---- flush: entry e of the run goes to global position base + e ------------------------------
-            if (mode == UGS_MODE_SAMPLE && !use_perm) {
-#pragma unroll 4
-                for (int e = lane; e < run; e += 32) {
-                    const u32 pk = s.stage[e];
-                    const i64 o = base + e;
-                    out_u[o] = (i64)(pk & 31u);
-                    out_v[o] = (i64)((pk >> 5) & 31u);
-                    out_src[o] = c0 + (i64)(pk >> 15);
+            if (EMIT_UNROLLED_FLUSH && mode == UGS_MODE_SAMPLE && !use_perm) {
+                i64* pu = out_u + base + lane;
+                i64* pv = out_v + base + lane;
+                i64* ps = out_src + base + lane;
+                const u32* sg = s.stage + lane;
+                int e = lane;
+                for (; e + 96 < run; e += 128) {  // four full warp-rows per trip, no bounds checks
+                    const u32 k0_ = sg[0], k1_ = sg[32], k2_ = sg[64], k3_ = sg[96];
+                    pu[0] = (i64)(k0_ & 31u); pu[32] = (i64)(k1_ & 31u); pu[64] = (i64)(k2_ & 31u); pu[96] = (i64)(k3_ & 31u);
+                    pv[0] = (i64)((k0_ >> 5) & 31u); pv[32] = (i64)((k1_ >> 5) & 31u);
+                    pv[64] = (i64)((k2_ >> 5) & 31u); pv[96] = (i64)((k3_ >> 5) & 31u);
+                    ps[0] = c0 + (i64)(k0_ >> 15); ps[32] = c0 + (i64)(k1_ >> 15);
+                    ps[64] = c0 + (i64)(k2_ >> 15); ps[96] = c0 + (i64)(k3_ >> 15);
+                    pu += 128; pv += 128; ps += 128; sg += 128;
+                }
+                for (; e < run; e += 32) {
+                    const u32 pk = sg[0];
+                    pu[0] = (i64)(pk & 31u);
+                    pv[0] = (i64)((pk >> 5) & 31u);
+                    ps[0] = c0 + (i64)(pk >> 15);
+                    pu += 32; pv += 32; ps += 32; sg += 32;
                 }
             } else {
 #pragma unroll 2
@@ -538,10 +584,9 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         }
         // un-set this tile's members so the map is all-0xFF again
         if (walk) {
-            for (int j = 0; j < k; ++j) {
-                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                s.lmap[lane][v] = (unsigned char)0xFF;
-            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)0xFF;
         }
     }
     (void)total;

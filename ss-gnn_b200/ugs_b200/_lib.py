@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SO = os.path.join(HERE, "libugs_b200.so")
+SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
 SOURCES = ["ugs_preproc.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
