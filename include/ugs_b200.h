@@ -151,6 +151,23 @@ int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m,
                     void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
                     const int64_t* nodes, int64_t* edge_ptr, void* stream);
 
+/* ---- epsilon-uniform variant (reference src/samplers/epsilon_uniform_sampler) --------------------
+ * Same workspace as the UGS path (ugs_segment_batch + ugs_preproc_batch); only the multigraph CSR is used.
+ * ugs_eps_sample_batch: random frontier growth + rejection min(1, eps/(w+eps)), <= max(10, 10/eps) attempts
+ * (epsilon_uniform_sampler.cpp:18-84,225-257); writes SORTED node rows (:256; -1 rows when every attempt failed),
+ * per-sample column counts scanned into edge_ptr, sample_ptr = g*m. counters[UGS_CTR_TRIALS] = growth attempts,
+ * counters[UGS_CTR_INCOMPLETE] = failed rows.
+ * ugs_eps_emit_edges: every batch column with both endpoints in the sample, in column order, src = the column
+ * (:267-290); mode "sample" = positions in the sorted row, other modes = batch-global node ids (:279-285). */
+int ugs_eps_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                         uint64_t graph_index_base, double epsilon, int64_t n_general, void* workspace,
+                         const ugs_layout* L, void* scratch, size_t scratch_bytes, int64_t* nodes,
+                         int64_t* edge_ptr, int64_t* sample_ptr, void* stream);
+int ugs_eps_emit_edges(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
+                       int64_t m, int k, int mode, const int64_t* perm, int64_t n_general, const void* workspace,
+                       const ugs_layout* L, const int64_t* nodes, const int64_t* edge_ptr, int64_t total,
+                       int64_t* edge_index_out, int64_t* edge_src_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

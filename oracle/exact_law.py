@@ -79,3 +79,45 @@ def chi_square(counts: dict, law: dict, total: int):
         stat += (o - e) ** 2 / e
     extra = sum(c for key, c in counts.items() if key not in law)
     return stat, len(law) - 1, extra
+
+
+def p_epsilon(rows, k: int, eps: float, max_attempts=None):
+    """Exact law of one output row of the epsilon_uniform sampler (SURVEY.md Appendix A.9,
+    epsilon_uniform_sampler.cpp:18-84,225-257). rows = adjacency lists WITH duplicates.
+    Returns {frozenset(S): prob, (): prob of an all -1 row}."""
+    n = len(rows)
+    if max_attempts is None:
+        max_attempts = max(10, int(10.0 / eps))
+    acc = defaultdict(float)  # per-attempt accepted mass per node set
+
+    def rec(S, frontier, w, p, depth):
+        if len(S) == k:
+            a = min(1.0, eps / (w + eps))
+            acc[frozenset(S)] += p * a
+            return
+        if not frontier or depth > 100 * k:
+            return  # growth failure: the attempt is wasted
+        F = len(frontier)
+        for fi, u in enumerate(frontier):
+            cand = [v for v in rows[u] if v not in S]
+            if not cand:
+                rec(S, frontier[:fi] + frontier[fi + 1:], w, p / F, depth + 1)
+                continue
+            C = len(cand)
+            mult = defaultdict(int)
+            for v in cand:
+                mult[v] += 1
+            for v, c in mult.items():
+                rec(S + [v], frontier + [v], w * (1.0 / (F + 1)) * (1.0 / C), p / F * c / C, depth + 1)
+
+    if n >= k:
+        for s in range(n):
+            rec([s], [s], 1.0 / n, 1.0 / n, 0)
+    A = sum(acc.values())
+    out = {}
+    if A > 0:
+        scale = (1.0 - (1.0 - A) ** max_attempts) / A
+        for key, v in acc.items():
+            out[key] = v * scale
+    out[()] = (1.0 - A) ** max_attempts if A < 1 else 0.0
+    return out

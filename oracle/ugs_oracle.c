@@ -505,3 +505,7 @@ void oracle_batch_free(OBatch* B) {
     if (!B) return;
     free(B->nodes); free(B->edge_u); free(B->edge_v); free(B->edge_ptr); free(B->sample_ptr); free(B->edge_src); free(B);
 }
+
+/* raw CSR accessors (used by eps_oracle.c, which shares the adjacency-with-duplicates rows) */
+const i64* oracle_preproc_indptr(const OPreproc* P) { return P->indptr; }
+const i32* oracle_preproc_indices(const OPreproc* P) { return P->indices; }

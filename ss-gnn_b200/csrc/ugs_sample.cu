@@ -680,6 +680,10 @@ static int run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, W
     return UGS_OK;
 }
 
+int ugs_run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& w, cudaStream_t st) {
+    return run_scan(edge_ptr, B, scratch, scratch_bytes, w, st);
+}
+
 static inline void small_items(int64_t m, int* tiles_per_item, int64_t* items_per_graph) {
     const int64_t ntiles = (m + 31) / 32;
     int tpi = (int)(ntiles < 4 ? (ntiles < 1 ? 1 : ntiles) : 4);

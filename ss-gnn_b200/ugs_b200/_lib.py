@@ -16,6 +16,7 @@ HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "
 EXPORTS = [
     "ugs_abi_version", "ugs_launch_count", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
     "ugs_preproc_batch", "ugs_sample_scratch_bytes", "ugs_sample_batch", "ugs_emit_edges", "ugs_count_edges",
+    "ugs_eps_sample_batch", "ugs_eps_emit_edges",
 ]
 
 
@@ -72,6 +73,8 @@ def lib():
     L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
+    L.ugs_eps_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ctypes.c_double, i64, vp, LP, vp, sz, vp, vp, vp, vp]
+    L.ugs_eps_emit_edges.argtypes = [vp, i64, vp, i64, i64, i64, ci, ci, vp, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     _LIB = L
     return L
 

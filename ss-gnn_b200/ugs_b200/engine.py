@@ -148,6 +148,50 @@ class DeviceBatch:
                                             total, _ptr(edge_index), _ptr(edge_src), _stream()))
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
 
+    def sample_epsilon(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
+                       epsilon: float = 0.1, graph_index_base: int = 0, given_nodes=None):
+        """epsilon_uniform_sampler.sample_batch on the device (same 5-tuple layout, SORTED node rows).
+        given_nodes: skip sampling and extract edges for these rows (pins the extraction stage)."""
+        L = _lib.lib()
+        if not (epsilon > 0.0 and epsilon <= 1.0):
+            raise RuntimeError("epsilon must be in (0, 1]")
+        k = self.k if k is None else int(k)
+        m = int(m)
+        G = max(self.G, 0)
+        dev = self.device
+        md = MODES.get(mode, 2)  # any mode other than "sample" emits batch-global ids (:279-285)
+        with torch.cuda.device(dev):
+            edge_ptr = torch.empty(G * m + 1, dtype=torch.int64, device=dev)
+            sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+            sbytes = int(L.ugs_sample_scratch_bytes(G, m))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            if given_nodes is None:
+                nodes = torch.empty((G * m, k), dtype=torch.int64, device=dev)
+                _lib.check(L.ugs_eps_sample_batch(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
+                                                  graph_index_base, float(epsilon), self.n_general, _ptr(self.ws),
+                                                  ctypes.byref(self.layout), _ptr(scratch), sbytes, _ptr(nodes),
+                                                  _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
+            else:
+                nodes = given_nodes.to(dev).contiguous()
+                # counts for caller-provided rows: CSR entries between members / 2 == columns inside the sample
+                _lib.check(L.ugs_count_edges(_ptr(self.ptr), G, self.node_base, m, k, self.n_general, _ptr(self.ws),
+                                             ctypes.byref(self.layout), _ptr(scratch), sbytes, _ptr(nodes),
+                                             _ptr(edge_ptr), _stream()))
+                edge_ptr //= 2
+                sample_ptr = torch.arange(G + 1, dtype=torch.int64, device=dev) * m
+            info = self.info()
+            total = int(edge_ptr[-1].item()) if given_nodes is not None else info[CTR["total_edges"]]
+            stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
+                         n_trials=info[CTR["trials"]], n_skipped_graphs=self.n_skipped,
+                         n_general_graphs=self.n_general)
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_eps_emit_edges(_ptr(self.edge_index), self.E, _ptr(self.ptr), G, self.node_base, m, k, md,
+                                            _ptr(self.perm), self.n_general, _ptr(self.ws), ctypes.byref(self.layout),
+                                            _ptr(nodes), _ptr(edge_ptr), total, _ptr(edge_index), _ptr(edge_src),
+                                            _stream()))
+        return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
+
     def extract(self, nodes: torch.Tensor, m: int, k: int | None = None, mode: str = "sample"):
         """Induced-edge extraction (A.7) for caller-provided node rows [G*m,k] (batch-global ids, -1 pad)."""
         L = _lib.lib()
