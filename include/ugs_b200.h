@@ -77,6 +77,7 @@ typedef struct ugs_layout {
     size_t suf;        /* uint64 [NT]    by position: {v : index_of[v] >= vi} (bitmask path only)        */
     size_t csr_idx;    /* int32  [2E]    neighbour local id                        (Preproc::indices)    */
     size_t csr_col;    /* int32  [2E]    batch-global source column                (edge_col_of_csr_pos -> g_edge2global) */
+    size_t gaux;       /* double [G]     per-graph acceptance constant C of UGS_VARIANT_UNIFORM                  */
 } ugs_layout;
 
 typedef struct ugs_ginfo {
@@ -150,6 +151,15 @@ int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, 
 int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
                     void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
                     const int64_t* nodes, int64_t* edge_ptr, void* stream);
+
+/* ---- exact-uniform accept/reject variant (not in the reference, see oracle/uni_oracle.c) ---------
+ * ugs_preproc_uniform: call after ugs_preproc_batch. Replaces order / suffix_deg / suf / bucket_b / cum / Z by
+ * the degree-dominating-order tables of the uniform mode and writes the acceptance constant C per graph.
+ * Bitmask path only: every sampled graph must have <= 64 nodes and k <= 8 (UGS_ELIMIT otherwise).
+ * Then ugs_sample_batch(variant = UGS_VARIANT_UNIFORM) and ugs_emit_edges as usual. */
+#define UGS_UNIFORM_MAX_TRIALS 4096
+int ugs_preproc_uniform(const int64_t* ptr, int64_t G, int64_t node_base, int k, int64_t n_general, void* workspace,
+                        const ugs_layout* L, void* stream);
 
 /* ---- epsilon-uniform variant (reference src/samplers/epsilon_uniform_sampler) --------------------
  * Same workspace as the UGS path (ugs_segment_batch + ugs_preproc_batch); only the multigraph CSR is used.

@@ -18,10 +18,10 @@ MODES = {"sample": 0, "graph": 1, "global": 2}
 
 def build(force: bool = False) -> str:
     out = os.path.join(HERE, "libugs_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ugs_oracle.c", "eps_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("ugs_oracle.c", "eps_oracle.c", "uni_oracle.c")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        subprocess.check_call(["gcc", "-O3", "-std=c11", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"])
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-std=c11", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"])
     return out
 
 
@@ -158,3 +158,65 @@ def sample_batch(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample"
     finally:
         L.oracle_batch_free(h)
     return nodes, ei, eptr, sptr, esrc
+
+
+class UniformTables:
+    """Tables of the exact-uniform accept/reject mode (oracle/uni_oracle.c) for one graph given its CSR."""
+
+    def __init__(self, edge_index, num_nodes: int, k: int):
+        self._P = Preproc(edge_index, num_nodes, k)
+        d = self._P.dump()
+        self._indptr, self._indices = d["indptr"], d["indices"]
+        L = lib()
+        L.uni_oracle_create.restype = ctypes.c_void_p
+        L.uni_oracle_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.uni_oracle_free.argtypes = [ctypes.c_void_p]
+        L.uni_oracle_dump.argtypes = [ctypes.c_void_p] * 7
+        L.uni_oracle_sample_nodes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
+                                              ctypes.c_void_p, ctypes.c_void_p]
+        self.n, self.k = int(num_nodes), int(k)
+        self._h = L.uni_oracle_create(_p(self._indptr), _p(self._indices), self.n, self.k)
+        if not self._h:
+            raise RuntimeError("uniform mode needs n <= 64 and k <= 8")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().uni_oracle_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def dump(self):
+        n = self.n
+        d = dict(order=np.zeros(n, np.int32), dsuf=np.zeros(n, np.int32), suf=np.zeros(n, np.uint64),
+                 b=np.zeros(n, np.float64), cum=np.zeros(n, np.float64))
+        zc = np.zeros(2, np.float64)
+        lib().uni_oracle_dump(self._h, _p(d["order"]), _p(d["dsuf"]), _p(d["suf"]), _p(d["b"]), _p(d["cum"]), _p(zc))
+        d["Z"], d["C"] = float(zc[0]), float(zc[1])
+        return d
+
+    def sample_nodes(self, m: int, seed: int = 42, graph_index: int = 0):
+        out = np.full((m, self.k), -1, np.int32)
+        trials = np.zeros(1, np.int64)
+        lib().uni_oracle_sample_nodes(self._h, m, seed & (2 ** 64 - 1), graph_index, _p(out), _p(trials))
+        return out, int(trials[0])
+
+
+def sample_batch_uniform(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample", seed: int = 42,
+                         graph_index_base: int = 0):
+    """Batch driver of the uniform mode: nodes per graph from UniformTables, edges by the reference extraction."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    ptr = np.asarray(ptr, dtype=np.int64)
+    G = len(ptr) - 1
+    nodes = np.full((G * m_per_graph, k), -1, np.int64)
+    for g in range(G):
+        lo, hi = int(ptr[g]), int(ptr[g + 1])
+        n = hi - lo
+        if n <= 0 or n < k:
+            continue
+        msk = (ei[0] >= lo) & (ei[0] < hi) & (ei[1] >= lo) & (ei[1] < hi)
+        T = UniformTables(ei[:, msk] - lo, n, k)
+        rows, _ = T.sample_nodes(m_per_graph, seed, graph_index_base + g)
+        nodes[g * m_per_graph:(g + 1) * m_per_graph] = np.where(rows >= 0, rows + lo, -1)
+    return sample_batch(ei, ptr, m_per_graph, k, mode, seed, graph_index_base, given_nodes=nodes)

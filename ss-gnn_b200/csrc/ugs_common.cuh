@@ -45,6 +45,7 @@ struct WS {
     u64* suf;
     i32* csr_idx;
     i32* csr_col;
+    double* gaux;
 };
 
 static inline WS ws_views(void* base, const ugs_layout* L) {
@@ -65,6 +66,7 @@ static inline WS ws_views(void* base, const ugs_layout* L) {
     w.suf = (u64*)(b + L->suf);
     w.csr_idx = (i32*)(b + L->csr_idx);
     w.csr_col = (i32*)(b + L->csr_col);
+    w.gaux = (double*)(b + L->gaux);
     return w;
 }
 

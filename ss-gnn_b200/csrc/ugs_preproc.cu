@@ -681,6 +681,7 @@ extern "C" int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout
     L->suf = take(sizeof(u64) * (size_t)(NT + 1));
     L->csr_idx = take(sizeof(i32) * (size_t)(2 * E + 1));
     L->csr_col = take(sizeof(i32) * (size_t)(2 * E + 1));
+    L->gaux = take(sizeof(double) * (size_t)(G + 1));
     L->total_bytes = off;
     return UGS_OK;
 }

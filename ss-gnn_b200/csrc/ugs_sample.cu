@@ -655,6 +655,9 @@ k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mod
 // =====================================================================================================
 // Host launchers
 // =====================================================================================================
+int ugs_launch_sample_uniform(const i64* ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, i64 n_general,
+                              WS& w, i64* nodes, i64* edge_ptr, i64* sample_ptr, cudaStream_t st);  // ugs_variants.cu
+
 static int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -699,7 +702,7 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
     if (m < 0) return ugs_set_error(UGS_EINVAL, "m_per_graph must be >= 0");
-    if (variant != UGS_VARIANT_REF) return ugs_set_error(UGS_EINVAL, "unknown variant %d", variant);
+    if (variant != UGS_VARIANT_REF && variant != UGS_VARIANT_UNIFORM) return ugs_set_error(UGS_EINVAL, "unknown variant %d", variant);
     if (m >= (1ll << 32)) return ugs_set_error(UGS_ELIMIT, "m_per_graph must be < 2^32");
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
@@ -712,6 +715,12 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         return UGS_OK;
     }
     if (!nodes) return ugs_set_error(UGS_EINVAL, "nodes is NULL");
+    if (variant == UGS_VARIANT_UNIFORM) {
+        const int rc = ugs_launch_sample_uniform(ptr, G, node_base, m, k, seed, graph_index_base, n_general, w, nodes,
+                                                 edge_ptr, sample_ptr, st);
+        if (rc != UGS_OK) return rc;
+        return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
+    }
     int tpi; int64_t ipg;
     small_items(m, &tpi, &ipg);
     {

@@ -596,3 +596,323 @@ extern "C" int ugs_eps_emit_edges(const int64_t* edge_index, int64_t E, const in
     }
     return UGS_OK;
 }
+
+// =====================================================================================================
+// Exact-uniform accept/reject variant (rule stated in oracle/uni_oracle.c). Bitmask path only.
+// =====================================================================================================
+#define UNI_WARPS 8
+
+// One warp per graph: degree-dominating order and its tables, overwriting the reference-order tables.
+__global__ void __launch_bounds__(UNI_WARPS * 32)
+k_uniform_tables_small(const i64* __restrict__ ptr, i64 G, i64 node_base, int k, WS w) {
+    __shared__ u64 s_adj[UNI_WARPS][64];
+    __shared__ u64 s_suf[UNI_WARPS][64];
+    __shared__ double s_b[UNI_WARPS][64];
+    __shared__ unsigned char s_order[UNI_WARPS][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 g = (i64)blockIdx.x * UNI_WARPS + warp;
+    if (g >= G) return;
+    ugs_ginfo gi = w.ginfo[g];
+    if (gi.cls != 1) return;
+    const i64 lo = ptr[g];
+    const int n = (int)(ptr[g + 1] - lo);
+    const i64 nb = lo - node_base;
+    u64 a0 = 0, a1 = 0;  // simple adjacency (no self bit) of vertices lane and lane+32
+    if (lane < n) a0 = w.adj[nb + lane] & ~(1ull << lane);
+    if (lane + 32 < n) a1 = w.adj[nb + lane + 32] & ~(1ull << (lane + 32));
+    s_adj[warp][lane] = a0; s_adj[warp][lane + 32] = a1;
+    u64 rem = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+    int my_d0 = 0, my_d1 = 0;  // dsuf of positions lane / lane+32 (filled as they are removed)
+    for (int vi = 0; vi < n; ++vi) {
+        int key0 = ((rem >> lane) & 1ull) ? (__popcll(a0 & rem) * 64 + (63 - lane)) : -1;
+        int key1 = ((rem >> (lane + 32)) & 1ull) ? (__popcll(a1 & rem) * 64 + (63 - (lane + 32))) : -1;
+        int key = max(key0, key1);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) key = max(key, __shfl_xor_sync(FULL_MASK, key, off));
+        const int v = 63 - (key & 63), d = key >> 6;
+        if (lane == (vi & 31)) {
+            s_order[warp][vi] = (unsigned char)v;
+            s_suf[warp][vi] = rem;
+            if (vi < 32) my_d0 = d; else my_d1 = d;
+        }
+        rem &= ~(1ull << v);
+    }
+    __syncwarp();
+    // reachability, weights, acceptance bound per position
+    double qmin = 1e300;
+    int lastv = -1, n0 = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int vi = lane + 32 * h;
+        double b = 0.0;
+        if (vi < n) {
+            const int v = s_order[warp][vi];
+            const u64 sufm = s_suf[warp][vi];
+            u64 vis = 1ull << v, expd = 0;
+            bool reach = false;
+            for (int it = 0; it < k; ++it) {
+                if (__popcll(vis) >= k) { reach = true; break; }
+                const u64 fr = vis & ~expd;
+                if (!fr) break;
+                const int u = __ffsll((long long)fr) - 1;
+                expd |= 1ull << u;
+                vis |= s_adj[warp][u] & sufm;
+            }
+            if (reach) {
+                const int dd = h ? my_d1 : my_d0;
+                const int d = dd > 1 ? dd : 1;
+                b = 1.0;
+                for (int t = 0; t < k - 1; ++t) b *= (double)d;
+                double den = 1.0;
+                const int nsuf = n - vi;
+                for (int i = 1; i <= k - 1; ++i) { const int a = i * d, c = nsuf - i; den *= (double)(a < c ? a : c); }
+                const double q = b / den;
+                qmin = fmin(qmin, q);
+                lastv = vi; n0++;
+            }
+            w.order[nb + vi] = v;
+            w.index_of[nb + v] = vi;
+            w.suffix_deg[nb + vi] = h ? my_d1 : my_d0;
+            w.suf[nb + vi] = sufm;
+            w.bucket_b[nb + vi] = b;
+        }
+        s_b[warp][vi] = b;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        qmin = fmin(qmin, __shfl_xor_sync(FULL_MASK, qmin, off));
+        lastv = max(lastv, __shfl_xor_sync(FULL_MASK, lastv, off));
+        n0 += __shfl_xor_sync(FULL_MASK, n0, off);
+    }
+    // running sums (exact while the total is <= 2^53, see k_preproc_small)
+    const double p0 = s_b[warp][2 * lane], p1 = s_b[warp][2 * lane + 1];
+    double incl = p0 + p1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double y = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += y;
+    }
+    const double total = __shfl_sync(FULL_MASK, incl, 31);
+    double cum0, cum1, Z;
+    if (total <= 9007199254740992.0) {
+        const double excl = incl - (p0 + p1);
+        cum0 = excl + p0; cum1 = cum0 + p1; Z = total;
+    } else {
+        double run = 0.0; cum0 = cum1 = 0.0;
+        for (int vi = 0; vi < 64; ++vi) {
+            run += s_b[warp][vi];
+            if (vi == 2 * lane) cum0 = run;
+            if (vi == 2 * lane + 1) cum1 = run;
+        }
+        Z = run;
+    }
+    if (2 * lane < n) w.cum[nb + 2 * lane] = cum0;
+    if (2 * lane + 1 < n) w.cum[nb + 2 * lane + 1] = cum1;
+    if (lane == 0) {
+        gi.Z = Z; gi.level = 0; gi.n_eligible = n0; gi.last_viable = lastv;
+        w.ginfo[g] = gi;
+        w.gaux[g] = (n0 > 0) ? qmin : 0.0;
+    }
+}
+
+struct __align__(16) UniSamp {
+    u64 adj[64];
+    u64 suf[64];
+    double cum[64];
+    double b[64];
+    unsigned char tile[32][16];
+    unsigned char order[64];
+    unsigned short rowptr[66];
+    unsigned char idx[2 * UGS_SMALL_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(UNI_WARPS * 32)
+k_sample_uniform_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
+                       int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
+                       i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
+    extern __shared__ __align__(16) unsigned char uni_smem_raw[];
+    UniSamp* sm_all = reinterpret_cast<UniSamp*>(uni_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const i64 item = (i64)blockIdx.x * UNI_WARPS + warp;
+    const i64 g = item / items_per_graph;
+    if (g >= G) return;
+    const int chunk = (int)(item - g * items_per_graph);
+    if (chunk == 0 && lane == 0) {
+        sample_ptr[g + 1] = (g + 1) * m;
+        if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
+    }
+    const ugs_ginfo gi = w.ginfo[g];
+    const int ntiles = (int)((m + 31) >> 5);
+    const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
+    const i64 lo = ptr[g];
+    const int r32 = 32 % k, q32 = 32 / k;
+    if (gi.cls != 1) {  // skipped graphs (n < k); general-path graphs are rejected on the host
+        for (int t = t0; t < t1; ++t) {
+            const i64 s0 = g * m + (i64)t * 32;
+            const int nv = (int)min((i64)32, m - (i64)t * 32);
+            for (int e = lane; e < nv * k; e += 32) nodes_out[s0 * k + e] = -1;
+            if (lane < nv) edge_ptr[1 + s0 + lane] = 0;
+        }
+        return;
+    }
+    UniSamp& s = sm_all[warp];
+    const int n = (int)(ptr[g + 1] - lo);
+    const i64 nb = lo - node_base;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < n) {
+            s.adj[v] = w.adj[nb + v] & ~(1ull << v);
+            s.suf[v] = w.suf[nb + v];
+            s.cum[v] = w.cum[nb + v];
+            s.b[v] = w.bucket_b[nb + v];
+            s.order[v] = (unsigned char)w.order[nb + v];
+        }
+    }
+    {
+        const u32* rp = w.rowptr + nb + g;
+        const i32* ci = w.csr_idx + 2 * w.cstart[g];
+        for (int v = lane; v <= n; v += 32) s.rowptr[v] = (unsigned short)rp[v];
+        for (int p = lane; p < gi.nnz; p += 32) s.idx[p] = (unsigned char)ci[p];
+    }
+    __syncwarp();
+    const double C = w.gaux[g];
+    const u64 gidx = gbase + (u64)g;
+    const int full = (1 << (k - 1)) - 1;
+    unsigned long long trials = 0, n_fail = 0;
+
+    for (int t = t0; t < t1; ++t) {
+        const i64 i = (i64)t * 32 + lane;
+        const bool active = i < m;
+        u64 nlo = ~0ull, nhi = ~0ull;
+        i64 cnt = 0;
+        if (active) {
+            bool ok = false;
+            int mem[8];
+            u64 S = 0;
+            if (gi.Z > 0.0) {
+                for (int a = 0; a < UGS_UNIFORM_MAX_TRIALS && !ok; ++a) {
+                    WordStream rs; rs.init((u32)i, gidx, (u32)a, seed);
+                    rs.c3 = 0x40000000u | (u32)a;
+                    trials++;
+                    const u32 w0 = rs.next(), w1 = rs.next();
+                    const double x = root_x(w0, w1, gi.Z);
+                    int lo_ = 0, hi_ = n - 1;
+                    while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (s.cum[mid] > x) hi_ = mid; else lo_ = mid + 1; }
+                    if (!(s.cum[lo_] > x)) lo_ = gi.last_viable;
+                    const int root_vi = lo_;
+                    const u64 sufm = s.suf[root_vi];
+                    mem[0] = s.order[root_vi];
+                    S = 1ull << mem[0];
+                    u64 nbr = s.adj[mem[0]];
+                    int size = 1;
+#pragma unroll
+                    for (int step = 1; step < 8; ++step) {
+                        if (step < k && size == step) {
+                            const u64 cut = nbr & sufm & ~S;
+                            const int c = __popcll(cut);
+                            if (c > 0) {
+                                const int x2 = select_bit64(cut, (int)__umulhi(rs.next(), (u32)c));
+                                S |= 1ull << x2; nbr |= s.adj[x2]; mem[step] = x2; size++;
+                            }
+                        }
+                    }
+                    if (size < k) continue;
+                    // p(S|r): push DP over subsets of S \ {r} (float32, same operation order as the oracle)
+                    float f[128];
+                    for (int q = 0; q <= full; ++q) f[q] = 0.0f;
+                    f[0] = 1.0f;
+                    for (int q = 0; q < full; ++q) {
+                        const float fq = f[q];
+                        if (fq == 0.0f) continue;
+                        u64 nb_ = s.adj[mem[0]], vm = 1ull << mem[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j)
+                            if (j < k && ((q >> (j - 1)) & 1)) { nb_ |= s.adj[mem[j]]; vm |= 1ull << mem[j]; }
+                        const u64 cut = nb_ & sufm & ~vm;
+                        const int c = __popcll(cut);
+                        if (c == 0) continue;
+                        const float qv = __fdiv_rn(fq, (float)c);
+#pragma unroll
+                        for (int j = 1; j < 8; ++j)
+                            if (j < k && !((q >> (j - 1)) & 1) && ((cut >> mem[j]) & 1ull))
+                                f[q | (1 << (j - 1))] = __fadd_rn(f[q | (1 << (j - 1))], qv);
+                    }
+                    const double den = __dmul_rn(s.b[root_vi], (double)f[full]);
+                    const double pa = C / den;
+                    const u32 a0 = rs.next(), a1 = rs.next();
+                    const u64 v53 = ((((u64)a0) << 32) | (u64)a1) >> 11;
+                    const double uu = (double)v53 * (1.0 / 9007199254740992.0);
+                    ok = (uu < pa);
+                }
+            }
+            if (ok) {
+                int c = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < k) {
+                        const int v = mem[j];
+                        pk_set(nlo, nhi, j, (u32)v);
+                        for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & 1ull);
+                    }
+                }
+                cnt = c;
+            } else {
+                n_fail++;
+            }
+        }
+        *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
+        __syncwarp();
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+        {
+            int sidx = lane / k, j = lane - sidx * k;
+            i64* out = nodes_out + s0 * k;
+            for (int e = lane; e < nv * k; e += 32) {
+                const unsigned char bv = s.tile[sidx][j];
+                out[e] = (bv == 0xFF) ? (i64)-1 : lo + (i64)bv;
+                j += r32; sidx += q32;
+                if (j >= k) { j -= k; sidx++; }
+            }
+        }
+        if (active) edge_ptr[1 + s0 + lane] = cnt;
+        __syncwarp();
+    }
+    trials = __reduce_add_sync(FULL_MASK, (unsigned)trials);
+    n_fail = __reduce_add_sync(FULL_MASK, (unsigned)n_fail);
+    if (lane == 0) {
+        if (trials) atomicAdd(&w.counters[UGS_CTR_TRIALS], trials);
+        if (n_fail) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], n_fail);
+    }
+}
+
+extern "C" int ugs_preproc_uniform(const int64_t* ptr, int64_t G, int64_t node_base, int k, int64_t n_general,
+                                   void* workspace, const ugs_layout* L, void* stream_) {
+    if (!workspace || !L) return ugs_set_error(UGS_EINVAL, "NULL workspace/layout");
+    if (k < 1 || k > 8) return ugs_set_error(UGS_ELIMIT, "the uniform variant supports k <= 8");
+    if (n_general > 0)
+        return ugs_set_error(UGS_ELIMIT, "the uniform variant supports graphs with <= %d nodes and <= %d edge columns",
+                             UGS_SMALL_MAX_N, UGS_SMALL_MAX_COLS);
+    if (G <= 0) return UGS_OK;
+    cudaStream_t st = (cudaStream_t)stream_;
+    WS w = ws_views(workspace, L);
+    k_uniform_tables_small<<<(unsigned)((G + UNI_WARPS - 1) / UNI_WARPS), UNI_WARPS * 32, 0, st>>>(ptr, G, node_base, k, w);
+    UGS_LAUNCH_CHECK("k_uniform_tables_small");
+    return UGS_OK;
+}
+
+// called from ugs_sample_batch (ugs_sample.cu) for UGS_VARIANT_UNIFORM
+int ugs_launch_sample_uniform(const i64* ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, i64 n_general,
+                              WS& w, i64* nodes, i64* edge_ptr, i64* sample_ptr, cudaStream_t st) {
+    if (k > 8 || n_general > 0) return ugs_set_error(UGS_ELIMIT, "the uniform variant supports k <= 8 and graphs with <= 64 nodes");
+    int tpi; int64_t ipg;
+    eps_items(m, &tpi, &ipg);
+    const int64_t items = G * ipg;
+    const size_t smem = sizeof(UniSamp) * UNI_WARPS;
+    UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_uniform_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sample_uniform_small<<<(unsigned)((items + UNI_WARPS - 1) / UNI_WARPS), UNI_WARPS * 32, smem, st>>>(
+        ptr, G, node_base, m, k, seed, gbase, tpi, ipg, w, nodes, edge_ptr, sample_ptr);
+    UGS_LAUNCH_CHECK("k_sample_uniform_small");
+    return UGS_OK;
+}

@@ -16,7 +16,7 @@ HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "
 EXPORTS = [
     "ugs_abi_version", "ugs_launch_count", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
     "ugs_preproc_batch", "ugs_sample_scratch_bytes", "ugs_sample_batch", "ugs_emit_edges", "ugs_count_edges",
-    "ugs_eps_sample_batch", "ugs_eps_emit_edges",
+    "ugs_eps_sample_batch", "ugs_eps_emit_edges", "ugs_preproc_uniform",
 ]
 
 
@@ -27,7 +27,7 @@ class LibraryMissing(RuntimeError):
 class Layout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "total_bytes", "cstart", "ginfo", "glist", "counters", "colkey", "rowptr", "order", "index_of",
-        "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col")]
+        "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col", "gaux")]
 
 
 def nvcc_command(out: str = SO):
@@ -73,6 +73,7 @@ def lib():
     L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
+    L.ugs_preproc_uniform.argtypes = [vp, i64, i64, ci, i64, vp, LP, vp]
     L.ugs_eps_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ctypes.c_double, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_eps_emit_edges.argtypes = [vp, i64, vp, i64, i64, i64, ci, ci, vp, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     _LIB = L

@@ -34,7 +34,7 @@ class DeviceBatch:
     """
 
     def __init__(self, edge_index: torch.Tensor, ptr: torch.Tensor, k: int, node_base: int, total_nodes: int,
-                 skip_lt_k: bool = True):
+                 skip_lt_k: bool = True, variant: str = "ref"):
         L = _lib.lib()
         if not (edge_index.is_cuda and ptr.is_cuda):
             raise RuntimeError("DeviceBatch needs CUDA tensors (there is no CPU path)")
@@ -75,6 +75,12 @@ class DeviceBatch:
             _lib.check(L.ugs_preproc_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.node_base,
                                            self.k, _ptr(self.perm), self.n_general, _ptr(self.ws),
                                            ctypes.byref(self.layout), _stream()))
+            self.variant = variant
+            if variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
+                _lib.check(L.ugs_preproc_uniform(_ptr(self.ptr), self.G, self.node_base, self.k, self.n_general,
+                                                 _ptr(self.ws), ctypes.byref(self.layout), _stream()))
+            elif variant != "ref":
+                raise RuntimeError(f"unknown variant {variant!r}")
 
     def _segment(self, skip_lt_k):
         _lib.check(_lib.lib().ugs_segment_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.k,
@@ -96,6 +102,7 @@ class DeviceBatch:
         "bucket_b": (torch.float64, lambda s: s.NT), "cum": (torch.float64, lambda s: s.NT),
         "adj": (torch.int64, lambda s: s.NT), "suf": (torch.int64, lambda s: s.NT),
         "csr_idx": (torch.int32, lambda s: 2 * s.E), "csr_col": (torch.int32, lambda s: 2 * s.E),
+        "gaux": (torch.float64, lambda s: s.G),
     }
 
     def view(self, name: str) -> torch.Tensor:
@@ -115,13 +122,16 @@ class DeviceBatch:
 
     # ------------------------------------------------------------------------------------------------
     def sample(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
-               graph_index_base: int = 0, variant: str = "ref", emit: bool = True):
+               graph_index_base: int = 0, variant: str | None = None, emit: bool = True):
         """Returns device tensors (nodes[G*m,k], edge_index[2,Ebar], edge_ptr[G*m+1], sample_ptr[G+1],
         edge_src[Ebar]) and the stats dict. One host sync (reading Ebar) between sampling and emission."""
         L = _lib.lib()
         if mode not in MODES:
             raise RuntimeError("mode must be one of: 'sample', 'graph', 'global'")
         k = self.k if k is None else int(k)
+        variant = self.variant if variant is None else variant
+        if variant != self.variant:
+            raise RuntimeError(f"this batch was preprocessed for variant {self.variant!r}")
         m = int(m)
         G = max(self.G, 0)
         dev = self.device
@@ -139,7 +149,7 @@ class DeviceBatch:
             total = info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
-                         n_general_graphs=self.n_general)
+                         n_general_graphs=self.n_general, n_trials=info[CTR["trials"]])
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
             if emit:
@@ -221,5 +231,5 @@ def sample_batch_device(edge_index, ptr, m_per_graph, k, mode="sample", seed=42,
     if total_nodes is None:
         pb = ptr[[0, -1]].tolist() if ptr.numel() > 0 else [0, 0]
         node_base, total_nodes = pb[0], pb[1] - pb[0]
-    b = DeviceBatch(edge_index, ptr, k, node_base, total_nodes)
-    return b.sample(m_per_graph, k, mode, seed, graph_index_base, variant)
+    b = DeviceBatch(edge_index, ptr, k, node_base, total_nodes, variant=variant)
+    return b.sample(m_per_graph, k, mode, seed, graph_index_base)

@@ -14,7 +14,9 @@ Differences from the reference, all deliberate:
   * no LRU preproc cache (the reference's key ignores k); preprocessing is recomputed per call on the GPU;
   * CUDA input tensors are accepted (outputs then stay on the device). With CPU inputs the outputs are CPU
     pinned int64 tensors exactly like the reference's (sampler.cpp:190); set UGS_B200_OUTPUT=cuda to keep
-    them on the GPU.
+    them on the GPU;
+  * UGS_B200_VARIANT=uniform switches sample_batch to the exact-uniform accept/reject mode (not in the reference:
+    its own law is not uniform).
 """
 from __future__ import annotations
 
@@ -147,7 +149,9 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
     with torch.cuda.device(dev):
         ei = edge_index.to(dev, non_blocking=True)
         p = ptr.to(dev, non_blocking=True)
-        b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0])
+        # UGS_B200_VARIANT=uniform selects the exact-uniform accept/reject mode; default = reference law
+        variant = os.environ.get("UGS_B200_VARIANT", "ref").lower()
+        b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0], variant=variant)
         outs, _stats = b.sample(int(m_per_graph), int(k), mode, int(seed))
         sample_batch.last_stats = _stats
         return tuple(outs if _want_cuda_out(edge_index) else _to_host(outs))

@@ -78,3 +78,22 @@ def test_reference_frequencies_follow_the_same_law():
         mod.destroy_preproc(h)
         stat, df, extra = xl.chi_square(Counter(_key(r) for r in rows), law, M)
         assert extra == 0 and stat < chi2.ppf(0.999, df), (name, stat, df)
+
+
+@pytest.mark.parametrize("name,und,n,k", CASES[:3] + [("toluene_k5", CASES[2][1], 10, 5)])
+def test_uniform_mode_oracle_is_uniform(name, und, n, k):
+    """oracle/uni_oracle.c (SURVEY A.8 accept/reject mode): chi-square against the uniform law over connected
+    induced k-subgraphs -- the property the reference's own UGS does not have."""
+    from oracle import exact_law as xl, ugs_oracle as uo
+    ei = bidir(und)
+    rows = xl.rows_from_dump(uo.Preproc(ei, n, k).dump())
+    subs = xl.connected_subsets(rows, k)
+    law = {s: 1.0 / len(subs) for s in subs}
+    M = 30000
+    nodes, trials = uo.UniformTables(ei, n, k).sample_nodes(M, seed=3)
+    assert (nodes >= 0).all() and trials >= M
+    stat, df, extra = xl.chi_square(Counter(_key(r) for r in nodes), law, M)
+    assert extra == 0 and stat < chi2.ppf(0.999, df), (name, stat, df)
+    # the reference law on the same graph is NOT uniform
+    stat_ref = xl.chi_square(Counter(_key(r) for r in uo.Preproc(ei, n, k).sample_nodes(M, seed=3)), law, M)[0]
+    assert stat_ref > chi2.ppf(0.999, df)
