@@ -91,7 +91,8 @@ typedef struct ugs_ginfo {
 } ugs_ginfo;
 
 /* counters[] slots */
-#define UGS_CTR_UNSORTED 0      /* !=0: columns are not graph-contiguous -> caller must sort (see below) */
+#define UGS_CTR_UNSORTED 0      /* bit0: columns not grouped by graph (sort them: perm); bit1: ptr decreasing;
+                                   bit2/bit3: the fast segmentation does not apply -> redo with fast = 0   */
 #define UGS_CTR_N_GENERAL 1
 #define UGS_CTR_MAX_N_GENERAL 2
 #define UGS_CTR_N_SKIPPED 3
@@ -113,10 +114,13 @@ int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout* out);
  * edge_index: [2,E] int64 row-major (row 1 at edge_index + E). ptr: [G+1] int64, non-decreasing.
  * perm: NULL, or int64[E] = a stable ordering of the columns by graph id produced after a first call
  * reported UGS_CTR_UNSORTED (columns are then read through perm).
+ * fast: 1 = assume graph-contiguous columns (every PyG batch): one binary search per graph instead of one per
+ *       column. The assumption is verified (counters[UGS_CTR_UNSORTED] bit 2 right away, bit 3 by the
+ *       preprocessing kernels); when a bit is set the caller must redo the batch with fast = 0.
  * skip_lt_k: 1 = graphs with fewer than k nodes produce all -1 rows (sample_batch, :132-143);
  *            0 = they are preprocessed and sampled at a relaxation level (handle API, sampler.cpp:125-146). */
 int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int k,
-                      int skip_lt_k, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream);
+                      int skip_lt_k, int fast, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream);
 
 /* Copies counters[0..7] to h_out (synchronises the stream). */
 int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);

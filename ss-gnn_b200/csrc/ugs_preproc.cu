@@ -43,6 +43,25 @@ __global__ void k_seg_bounds(const i32* __restrict__ colkey, i64 E, i64 G, i64* 
     for (i64 g = prev + 1; g <= cur; ++g) cstart[g] = j;
 }
 
+// Fast path for graph-contiguous batches (every PyG batch): cstart[g] = first column whose source node is
+// >= ptr[g], by one binary search per GRAPH over the columns. The result is only right if the columns are grouped
+// by graph; that is verified for free later (k_classify: monotone bounds covering [0,E); preproc kernels: every
+// column of a graph's range has its source inside the graph) and the caller falls back to the per-column path
+// (k_seg_keys + stable sort) when a check trips.
+__global__ void k_seg_fast(const i64* __restrict__ row0, i64 E, const i64* __restrict__ ptr, i64 G,
+                           i64* __restrict__ cstart) {
+    i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G + 1) return;
+    if (g == G + 1) { cstart[g] = E; return; }
+    const i64 target = ptr[g];
+    i64 lo = 0, hi = E;  // first j with row0[j] >= target
+    while (lo < hi) {
+        const i64 mid = (lo + hi) >> 1;
+        if (row0[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    cstart[g] = lo;
+}
+
 __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_lt_k, WS w) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -51,6 +70,8 @@ __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_l
     ugs_ginfo gi;
     gi.Z = 0.0; gi.nnz = 0; gi.level = -1; gi.n_eligible = 0; gi.last_viable = -1; gi.mult = 0;
     if (n < 0) atomicOr(&w.counters[UGS_CTR_UNSORTED], 2ull);  // ptr not non-decreasing
+    if (nc < 0 || (g == 0 && w.cstart[0] != 0) || (g == G - 1 && w.cstart[G] != w.cstart[G + 1]))
+        atomicOr(&w.counters[UGS_CTR_UNSORTED], 4ull);  // bounds do not tile [0,E): not graph-contiguous
     if (n <= 0 || (skip_lt_k && n < k)) {  // ugs_sampler_batch_extension.cpp:132 (batch driver only)
         gi.cls = 0;
         atomicAdd(&w.counters[UGS_CTR_N_SKIPPED], 1ull);
@@ -107,8 +128,10 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
     // ---- A.2 degrees + adjacency bitmask --------------------------------------------------------
     for (int c = lane; c < nc; c += 32) {
         const i64 j = perm ? perm[c0 + c] : c0 + c;
-        const i64 u = row0[j] - lo, v = row1[j] - lo;  // u is inside [0,n) by construction of colkey
-        const bool valid = (v >= 0) && (v < n);        // cross-graph / out-of-range columns are dropped (:53)
+        const i64 u = row0[j] - lo, v = row1[j] - lo;
+        const bool u_ok = (u >= 0) && (u < n);  // always true unless the fast segmentation was fooled
+        if (!u_ok) atomicOr(&w.counters[UGS_CTR_UNSORTED], 8ull);
+        const bool valid = u_ok && (v >= 0) && (v < n);  // cross-graph / out-of-range columns are dropped (:53)
         s.cu[c] = (unsigned char)u;
         s.cv[c] = valid ? (unsigned char)v : (unsigned char)0xFF;
         if (valid) {
@@ -424,6 +447,7 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
         for (i64 c = tid; c < nc; c += T_) {
             const i64 j = perm ? perm[c0 + c] : c0 + c;
             const i64 u = row0[j] - lo, v = row1[j] - lo;
+            if (u < 0 || u >= n) { atomicOr(&w.counters[UGS_CTR_UNSORTED], 8ull); continue; }
             if (v >= 0 && v < n) { atomicAdd(&iof[u], 1); atomicAdd(&iof[v], 1); }
         }
         __syncthreads();
@@ -440,7 +464,7 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
         for (i64 c = tid; c < nc; c += T_) {
             const i64 j = perm ? perm[c0 + c] : c0 + c;
             const i64 u = row0[j] - lo, v = row1[j] - lo;
-            if (v >= 0 && v < n) {
+            if (u >= 0 && u < n && v >= 0 && v < n) {
                 const u32 pu = rp[u] + (u32)atomicAdd(&ord[u], 1);
                 cidx[pu] = (i32)v; ccol[pu] = (i32)j;
                 const u32 pv = rp[v] + (u32)atomicAdd(&ord[v], 1);
@@ -687,7 +711,7 @@ extern "C" int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout
 }
 
 extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int k,
-                                 int skip_lt_k, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream_) {
+                                 int skip_lt_k, int fast, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream_) {
     if (!workspace || !L || (!ptr && G >= 0)) return ugs_set_error(UGS_EINVAL, "NULL workspace/layout/ptr");
     if (E > 0 && !edge_index) return ugs_set_error(UGS_EINVAL, "edge_index is NULL");
     if (k < 1) return ugs_set_error(UGS_EINVAL, "k must be >= 1");
@@ -696,12 +720,17 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
     WS w = ws_views(workspace, L);
     UGS_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(i64) * 16, st));
     const int T = 256;
-    if (E > 0) {
-        k_seg_keys<<<(unsigned)((E + T - 1) / T), T, 0, st>>>(edge_index, E, ptr, G, perm, w.colkey);
-        UGS_LAUNCH_CHECK("k_seg_keys");
+    if (fast && !perm) {
+        k_seg_fast<<<(unsigned)((G + 2 + T - 1) / T), T, 0, st>>>(edge_index, E, ptr, G, w.cstart);
+        UGS_LAUNCH_CHECK("k_seg_fast");
+    } else {
+        if (E > 0) {
+            k_seg_keys<<<(unsigned)((E + T - 1) / T), T, 0, st>>>(edge_index, E, ptr, G, perm, w.colkey);
+            UGS_LAUNCH_CHECK("k_seg_keys");
+        }
+        k_seg_bounds<<<(unsigned)((E + 1 + T - 1) / T), T, 0, st>>>(w.colkey, E, G, w.cstart, w.counters);
+        UGS_LAUNCH_CHECK("k_seg_bounds");
     }
-    k_seg_bounds<<<(unsigned)((E + 1 + T - 1) / T), T, 0, st>>>(w.colkey, E, G, w.cstart, w.counters);
-    UGS_LAUNCH_CHECK("k_seg_bounds");
     if (G > 0) {
         k_classify<<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, w);
         UGS_LAUNCH_CHECK("k_classify");

@@ -314,7 +314,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
 // In-place inclusive scan of the per-sample counts (single pass, decoupled look-back)
 // =====================================================================================================
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 8
+#define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -324,7 +324,7 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
     __shared__ i64 s_prefix;
     __shared__ unsigned int s_tile;
     unsigned long long* ticket = scratch;
-    volatile unsigned long long* status = scratch + 1;
+    volatile unsigned long long* status = scratch + 1;  // value << 2 | flag (1 = aggregate, 2 = inclusive prefix)
     if (threadIdx.x == 0) s_tile = (unsigned int)atomicAdd(ticket, 1ull);
     __syncthreads();
     const i64 tile = s_tile;
@@ -352,25 +352,33 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
         if (q < warp) warp_excl += x;
         block_total += x;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // decoupled look-back, one warp: 32 predecessors per step
         i64 prefix = 0;
         if (tile == 0) {
-            status[0] = ((unsigned long long)block_total << 2) | 2ull;
+            if (lane == 0) status[0] = ((unsigned long long)block_total << 2) | 2ull;
         } else {
-            status[tile] = ((unsigned long long)block_total << 2) | 1ull;
-            __threadfence();
+            if (lane == 0) status[tile] = ((unsigned long long)block_total << 2) | 1ull;
             i64 j = tile - 1;
             while (true) {
-                unsigned long long sv = status[j];
-                while ((sv & 3ull) == 0ull) sv = status[j];
-                prefix += (i64)(sv >> 2);
-                if ((sv & 3ull) == 2ull) break;
-                --j;
+                const i64 idx = j - lane;
+                unsigned long long sv = (idx >= 0) ? status[idx] : 2ull;  // before tile 0: prefix 0, inclusive
+                while (__any_sync(FULL_MASK, (sv & 3ull) == 0ull)) sv = (idx >= 0) ? status[idx] : 2ull;
+                const u32 incl_mask = __ballot_sync(FULL_MASK, (sv & 3ull) == 2ull);
+                const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest predecessor with a full prefix
+                i64 contrib = (lane <= first) ? (i64)(sv >> 2) : 0;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) contrib += __shfl_xor_sync(FULL_MASK, contrib, off);
+                prefix += contrib;
+                if (incl_mask) break;
+                j -= 32;
             }
-            status[tile] = ((unsigned long long)(prefix + block_total) << 2) | 2ull;
+            if (lane == 0) status[tile] = ((unsigned long long)(prefix + block_total) << 2) | 2ull;
         }
-        s_prefix = prefix;
-        if ((tile + 1) * SCAN_TILE >= B) counters[UGS_CTR_TOTAL_EDGES] = (unsigned long long)(prefix + block_total);
+        if (lane == 0) {
+            s_prefix = prefix;
+            if ((tile + 1) * SCAN_TILE >= B) counters[UGS_CTR_TOTAL_EDGES] = (unsigned long long)(prefix + block_total);
+        }
     }
     __syncthreads();
     i64 run = s_prefix + warp_excl + (incl - local);

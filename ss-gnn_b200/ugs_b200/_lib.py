@@ -65,7 +65,7 @@ def lib():
     L.ugs_last_error.restype = ctypes.c_char_p
     L.ugs_launch_count.restype = ctypes.c_uint64
     L.ugs_workspace_layout.argtypes = [i64, i64, i64, LP]
-    L.ugs_segment_batch.argtypes = [vp, i64, vp, i64, ci, ci, vp, vp, LP, vp]
+    L.ugs_segment_batch.argtypes = [vp, i64, vp, i64, ci, ci, ci, vp, vp, LP, vp]
     L.ugs_batch_info.argtypes = [vp, LP, vp, vp]
     L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, vp, LP, vp]
     L.ugs_sample_scratch_bytes.restype = sz

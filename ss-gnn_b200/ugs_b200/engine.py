@@ -57,17 +57,33 @@ class DeviceBatch:
         self.ws = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
         self.perm = None
         self._info_host = torch.empty(8, dtype=torch.int64).pin_memory()
+        self._skip_lt_k = skip_lt_k
+        self.variant = variant
+        if variant not in ("ref", "uniform"):
+            raise RuntimeError(f"unknown variant {variant!r}")
+        self._build(fast=True)
+
+    def _build(self, fast: bool):
+        """segment -> (sort columns by graph if needed) -> preprocess. `fast` assumes graph-contiguous columns
+        (every PyG batch); the kernels verify it and `_late_check` redoes the batch on the slow path otherwise."""
+        L = _lib.lib()
+        self.perm = None
+        self._fast = fast
         with torch.cuda.device(self.device):
-            self._segment(skip_lt_k)
+            self._segment(fast)
             info = self.info()
             if info[CTR["unsorted"]] & 2:
                 raise RuntimeError("ptr must be non-decreasing")
+            if fast and (info[CTR["unsorted"]] & 4):
+                self._fast = fast = False
+                self._segment(False)
+                info = self.info()
             if info[CTR["unsorted"]] & 1:
                 # Columns are not graph-contiguous (never the case for PyG batches): order them stably by
                 # graph id once and read them through `perm` from here on.
                 colkey = self.view("colkey")
                 self.perm = torch.sort(colkey, stable=True).indices.contiguous()
-                self._segment(skip_lt_k)
+                self._segment(False)
                 info = self.info()
             self.n_general = int(info[CTR["n_general"]])
             self.max_n_general = int(info[CTR["max_n_general"]])
@@ -75,16 +91,22 @@ class DeviceBatch:
             _lib.check(L.ugs_preproc_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.node_base,
                                            self.k, _ptr(self.perm), self.n_general, _ptr(self.ws),
                                            ctypes.byref(self.layout), _stream()))
-            self.variant = variant
-            if variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
+            if self.variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
                 _lib.check(L.ugs_preproc_uniform(_ptr(self.ptr), self.G, self.node_base, self.k, self.n_general,
                                                  _ptr(self.ws), ctypes.byref(self.layout), _stream()))
-            elif variant != "ref":
-                raise RuntimeError(f"unknown variant {variant!r}")
 
-    def _segment(self, skip_lt_k):
+    def _late_check(self, info) -> bool:
+        """True if the preprocessing kernels found a column outside its graph's range (the fast segmentation was
+        fooled by a batch that is not graph-contiguous): the batch has been rebuilt on the slow path, redo the op."""
+        if self._fast and (info[CTR["unsorted"]] & 8):
+            self._build(fast=False)
+            return True
+        return False
+
+    def _segment(self, fast):
         _lib.check(_lib.lib().ugs_segment_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.k,
-                                                1 if skip_lt_k else 0, _ptr(self.perm), _ptr(self.ws),
+                                                1 if self._skip_lt_k else 0, 1 if fast else 0, _ptr(self.perm),
+                                                _ptr(self.ws),
                                                 ctypes.byref(self.layout), _stream()))
 
     def info(self):
@@ -105,7 +127,13 @@ class DeviceBatch:
         "gaux": (torch.float64, lambda s: s.G),
     }
 
+    def _ensure_valid(self):
+        if self._fast:
+            self._late_check(self.info())
+
     def view(self, name: str) -> torch.Tensor:
+        if name != "colkey":
+            self._ensure_valid()
         dt, nfn = self._VIEWS[name]
         n = nfn(self)
         off = getattr(self.layout, name)
@@ -114,6 +142,7 @@ class DeviceBatch:
 
     def ginfo(self) -> dict:
         """Per-graph records as CPU tensors: Z, nnz, level, n_eligible, last_viable, mult, cls."""
+        self._ensure_valid()
         raw = self.ws[self.layout.ginfo:self.layout.ginfo + 32 * self.G].cpu()
         z = raw.view(torch.float64).view(self.G, 4)[:, 0].clone()
         ints = raw.view(torch.int32).view(self.G, 8)
@@ -146,6 +175,8 @@ class DeviceBatch:
                                           _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch), sbytes,
                                           _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
             info = self.info()
+            if self._late_check(info):
+                return self.sample(m, k, mode, seed, graph_index_base, variant, emit)
             total = info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
@@ -190,6 +221,8 @@ class DeviceBatch:
                 edge_ptr //= 2
                 sample_ptr = torch.arange(G + 1, dtype=torch.int64, device=dev) * m
             info = self.info()
+            if self._late_check(info):
+                return self.sample_epsilon(m, k, mode, seed, epsilon, graph_index_base, given_nodes)
             total = int(edge_ptr[-1].item()) if given_nodes is not None else info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_trials=info[CTR["trials"]], n_skipped_graphs=self.n_skipped,
@@ -216,7 +249,10 @@ class DeviceBatch:
             _lib.check(L.ugs_count_edges(_ptr(self.ptr), G, self.node_base, m, k, self.n_general, _ptr(self.ws),
                                          ctypes.byref(self.layout), _ptr(scratch), sbytes, _ptr(nodes),
                                          _ptr(edge_ptr), _stream()))
-            total = self.info()[CTR["total_edges"]]
+            info = self.info()
+            if self._late_check(info):
+                return self.extract(nodes, m, k, mode)
+            total = info[CTR["total_edges"]]
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
             _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,

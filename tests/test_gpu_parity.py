@@ -128,8 +128,8 @@ def test_unsorted_columns_take_the_perm_path(cuda_lib):
     perm = rng.permutation(ei.shape[1])
     ei2 = np.ascontiguousarray(ei[:, perm])
     b = _batch(ei2, ptr, 4)
+    _check_tables(b, ei2, ptr, 4)  # the first access notices the failed fast segmentation and rebuilds
     assert b.perm is not None
-    _check_tables(b, ei2, ptr, 4)
     outs, _ = b.sample(9, 4, "global", seed=1)
     ref = _oracle_batch(ei2, ptr, 9, 4, "global", 1)
     for a, r in zip(outs, ref):
@@ -200,3 +200,20 @@ def test_big_m_single_graph_and_large_scale_properties(cuda_lib):
     cnt = eptr[1:] - eptr[:-1]
     assert bool((cnt % 4 == 0).all()) and bool((cnt >= 4 * (k - 1)).all())
     assert stats["n_incomplete"] == 0
+
+
+def test_unsorted_columns_detected_late_by_sample(cuda_lib):
+    """Columns grouped by graph except for two swapped columns deep inside: the per-graph binary search may be
+    fooled, the preprocessing kernels notice a foreign column, and sample() redoes the batch on the slow path."""
+    rng = np.random.default_rng(17)
+    ei, ptr = random_batch(rng, 30, 5, 30, deg=2.0, weird=False)
+    g = np.searchsorted(ptr, ei[0], side="right") - 1
+    a = int(np.nonzero(g == 3)[0][1])
+    b_ = int(np.nonzero(g == 20)[0][1])
+    ei2 = ei.copy()
+    ei2[:, [a, b_]] = ei2[:, [b_, a]]
+    for m, k in ((5, 3),):
+        outs, _ = _batch(ei2, ptr, k).sample(m, k, "global", seed=2)
+        ref = _oracle_batch(ei2, ptr, m, k, "global", 2)
+        for x, r in zip(outs, ref):
+            assert np.array_equal(x.cpu().numpy(), r)
