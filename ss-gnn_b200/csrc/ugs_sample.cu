@@ -11,7 +11,9 @@
 #include "ugs_common.cuh"
 
 #define SAMP_WARPS 8
+#ifndef EMIT_WARPS
 #define EMIT_WARPS 8
+#endif
 
 // =====================================================================================================
 // Bitmask path: sample + count
@@ -26,14 +28,82 @@ struct __align__(16) SmallSamp {
     unsigned char idx[2 * UGS_SMALL_MAX_COLS];
 };
 
+// r-th set bit, for either mask width
+__device__ __forceinline__ int select_bit(u32 m, int r) { return select_bit32(m, r); }
+__device__ __forceinline__ int select_bit(u64 m, int r) { return select_bit64(m, r); }
+__device__ __forceinline__ int popc_m(u32 m) { return __popc(m); }
+__device__ __forceinline__ int popc_m(u64 m) { return __popcll(m); }
+
+// One sample: root draw (A.5), growth (A.6) and induced-edge count (A.7). MaskT = u32 when the graph has at
+// most 32 vertices (every mask operation is then a single 32-bit instruction), u64 otherwise. KT > 0 fixes k at
+// compile time so that the growth loop unrolls and the Philox refills land at fixed steps.
+template <typename MaskT, int KT>
+__device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& gi, int n, int k, u32 i, u32 c2, u32 c3,
+                                           u32 k0, u32 k1, u64& nlo, u64& nhi, i64& cnt, int& n_incomplete) {
+    const int kk = KT ? KT : k;
+    Philox4 r = philox4x32_10(i, 0u, c2, c3, k0, k1);
+    const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
+    int a = 0, b = n - 1;
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (s.cum[mid] > x) b = mid; else a = mid + 1;
+    }
+    if (gi.level == 0 && !(s.cum[a] > x)) a = gi.last_viable;
+    const int root_vi = a;
+    const int v0 = s.order[root_vi];
+    const MaskT sufm = (MaskT)s.suf[root_vi];
+    MaskT S = (MaskT)1 << v0;
+    MaskT nbr = (MaskT)s.adj[v0];
+    nlo = (nlo & ~0xFFull) | (u64)v0;
+    int size = 1;
+#pragma unroll
+    for (int step = 1; step < (KT ? KT : 16); ++step) {
+        if (step >= kk) break;
+        const MaskT cut = nbr & sufm & ~S;
+        const int c = popc_m(cut);
+        if (c == 0) break;
+        const int wsel = (step + 1) & 3;
+        if (wsel == 0) r = philox4x32_10(i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
+        const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
+        const int xnew = select_bit(cut, (int)__umulhi(wv, (u32)c));
+        S |= (MaskT)1 << xnew;
+        nbr |= (MaskT)s.adj[xnew];
+        if (step < 8) nlo = (nlo & ~(0xFFull << (8 * step))) | ((u64)xnew << (8 * step));
+        else nhi = (nhi & ~(0xFFull << (8 * (step - 8)))) | ((u64)xnew << (8 * (step - 8)));
+        size++;
+    }
+    if (size == kk) {
+        int c = 0;
+        if (gi.mult > 0) {
+#pragma unroll
+            for (int j = 0; j < (KT ? KT : 16); ++j) {
+                if (j >= kk) break;
+                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                c += popc_m((MaskT)s.adj[v] & S);
+            }
+            c *= gi.mult;
+        } else {
+            for (int j = 0; j < kk; ++j) {
+                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
+                for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & (MaskT)1);
+            }
+        }
+        cnt = c;
+    } else {
+        n_incomplete++;
+    }
+}
+
+template <int KT>
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
                int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
                i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
     __shared__ SmallSamp sm_all[SAMP_WARPS];
+    if (KT) k = KT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 item = (i64)blockIdx.x * SAMP_WARPS + warp;
-    const i64 g = item / items_per_graph;
+    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
     if (g >= G) return;
     const int chunk = (int)(item - g * items_per_graph);
     if (chunk == 0 && lane == 0) {
@@ -88,58 +158,8 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
         i64 cnt = 0;
         if (active) {
-            Philox4 r = philox4x32_10((u32)i, 0u, c2, c3, k0, k1);
-            // ---- root (A.5) ------------------------------------------------------------------------
-            const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z)
-                                             : (double)__umulhi(r.x, (u32)gi.n_eligible);
-            int a = 0, b = n - 1;
-            while (a < b) {
-                const int mid = (a + b) >> 1;
-                if (s.cum[mid] > x) b = mid; else a = mid + 1;
-            }
-            if (gi.level == 0 && !(s.cum[a] > x)) a = gi.last_viable;
-            const int root_vi = a;
-            // ---- growth (A.6) ----------------------------------------------------------------------
-            const int v0 = s.order[root_vi];
-            const u64 sufm = s.suf[root_vi];
-            u64 S = 1ull << v0;
-            u64 nbr = s.adj[v0];
-            nlo = (nlo & ~0xFFull) | (u64)v0;
-            int size = 1;
-            for (int step = 1; step < k; ++step) {
-                const u64 cut = nbr & sufm & ~S;
-                const int c = __popcll(cut);
-                if (c == 0) break;
-                const int wsel = (step + 1) & 3;
-                if (wsel == 0) r = philox4x32_10((u32)i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
-                const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
-                const int xnew = select_bit64(cut, (int)__umulhi(wv, (u32)c));
-                S |= 1ull << xnew;
-                nbr |= s.adj[xnew];
-                if (step < 8) nlo = (nlo & ~(0xFFull << (8 * step))) | ((u64)xnew << (8 * step));
-                else nhi = (nhi & ~(0xFFull << (8 * (step - 8)))) | ((u64)xnew << (8 * (step - 8)));
-                size++;
-            }
-            // ---- induced-edge count (A.7) ------------------------------------------------------------
-            if (size == k) {
-                if (gi.mult > 0) {
-                    int c = 0;
-                    for (int j = 0; j < k; ++j) {
-                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                        c += __popcll(s.adj[v] & S);
-                    }
-                    cnt = (i64)c * gi.mult;
-                } else {
-                    int c = 0;
-                    for (int j = 0; j < k; ++j) {
-                        const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                        for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & 1ull);
-                    }
-                    cnt = c;
-                }
-            } else {
-                n_incomplete++;
-            }
+            if (n <= 32) sample_one<u32, KT>(s, gi, n, k, (u32)i, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            else sample_one<u64, KT>(s, gi, n, k, (u32)i, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
         }
         // ---- coalesced output through the shared tile ------------------------------------------------
         *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
@@ -407,6 +427,12 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 #ifndef EMIT_MIN_BLOCKS
 #define EMIT_MIN_BLOCKS 3
 #endif
+#ifndef EMIT_PAIRWALK
+#define EMIT_PAIRWALK 0  // (measured slower) rows padded to an even number of entries; the walk handles two entries per step
+#endif
+#ifndef EMIT_ALU_LMAP
+#define EMIT_ALU_LMAP 0  // 1: membership + local index from registers (bit test + byte compare) instead of lmap[]
+#endif
 #define LMAP_STRIDE 68   // 17 words: the 32 per-sample rows start in 32 different banks
 
 struct __align__(16) SmallEmit {
@@ -414,7 +440,7 @@ struct __align__(16) SmallEmit {
     u32 rowrange[64];                       // byte offsets into ent[]: 2*rowptr[v] | 2*rowptr[v+1] << 16
     unsigned char tile[32][16];             // node rows as local ids (mode "global" only)
     unsigned char lmap[32][LMAP_STRIDE];    // local vertex id -> position inside its sample, 0xFF = not a member
-    unsigned short ent[2 * UGS_SMALL_MAX_COLS];  // CSR entry: neighbour id | payload << 6
+    unsigned short ent[2 * UGS_SMALL_MAX_COLS + (EMIT_PAIRWALK ? 64 : 0)];  // CSR entry: neighbour id | payload << 6
 };
 // payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
 // when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
@@ -449,11 +475,36 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
     {
         const u32* rp = w.rowptr + nb + g;
         const i32* ci = w.csr_idx + 2 * c0;
+#if EMIT_PAIRWALK
+        // pad every row to an even number of entries so that a row starts on a 4-byte boundary
+        const u32 lt = (1u << lane) - 1u;
+        const u32 r0 = (lane < n) ? rp[lane] : 0, r0e = (lane < n) ? rp[lane + 1] : 0;
+        const u32 r1 = (lane + 32 < n) ? rp[lane + 32] : 0, r1e = (lane + 32 < n) ? rp[lane + 33] : 0;
+        const u32 b0 = __ballot_sync(FULL_MASK, (r0e - r0) & 1u), b1 = __ballot_sync(FULL_MASK, (r1e - r1) & 1u);
+        const u32 ps0 = r0 + __popc(b0 & lt), ps1 = r1 + __popc(b0) + __popc(b1 & lt);
+        if (lane < n) {
+            s.rowrange[lane] = (ps0 << 1) | ((ps0 + (r0e - r0)) << 17);
+            for (u32 q = 0; q < r0e - r0; ++q) {
+                const u32 pp = r0 + q;
+                const u32 payload = use_perm ? pp : (u32)(gcol[pp] - (i32)c0);
+                s.ent[ps0 + q] = (unsigned short)((u32)ci[pp] | (payload << 6));
+            }
+        }
+        if (lane + 32 < n) {
+            s.rowrange[lane + 32] = (ps1 << 1) | ((ps1 + (r1e - r1)) << 17);
+            for (u32 q = 0; q < r1e - r1; ++q) {
+                const u32 pp = r1 + q;
+                const u32 payload = use_perm ? pp : (u32)(gcol[pp] - (i32)c0);
+                s.ent[ps1 + q] = (unsigned short)((u32)ci[pp] | (payload << 6));
+            }
+        }
+#else
         for (int v = lane; v < n; v += 32) s.rowrange[v] = (rp[v] << 1) | (rp[v + 1] << 17);
         for (int p = lane; p < gi.nnz; p += 32) {
             const u32 payload = use_perm ? (u32)p : (u32)(gcol[p] - (i32)c0);
             s.ent[p] = (unsigned short)((u32)ci[p] | (payload << 6));
         }
+#endif
         u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
 #pragma unroll
         for (int q = 0; q < LMAP_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
@@ -509,6 +560,17 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                 if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)j;
         }
 #endif
+#if EMIT_ALU_LMAP
+        u32 Slo = 0, Shi = 0;
+        if (walk) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < k) {
+                    const u32 v = (nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    if (v & 32u) Shi |= 1u << (v & 31u); else Slo |= 1u << v;
+                }
+        }
+#endif
         // balanced sub-batches: when the tile does not fit the staging buffer, aim for equal shares
         const int tile_total = (int)min(tile_end - __shfl_sync(FULL_MASK, my_lo, 0), (i64)0x7fffffff);
         const int nsplit = (tile_total + EMIT_STAGE - 1) / EMIT_STAGE;
@@ -528,6 +590,26 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                 int j = 0;
                 u32 rr = s.rowrange[nb4[0] & 0xFFu];
                 u32 p = rr & 0xFFFFu, pe = rr >> 16;  // byte offsets into ent[]
+#if EMIT_PAIRWALK && !EMIT_ALU_LMAP
+                while (true) {
+                    bool done = false;
+                    while (p >= pe) {
+                        if (++j == k) { done = true; break; }
+                        const u32 wsel = (j < 4) ? nb4[0] : (j < 8) ? nb4[1] : (j < 12) ? nb4[2] : nb4[3];
+                        rr = s.rowrange[(wsel >> (8 * (j & 3))) & 0xFFu];
+                        p = rr & 0xFFFFu; pe = rr >> 16;
+                        pj++;
+                    }
+                    if (done) break;
+                    const u32 two = *reinterpret_cast<const u32*>(entb + p);  // rows start 4-byte aligned
+                    const u32 e0 = two & 0xFFFFu, e1 = two >> 16;
+                    const u32 l0 = lrow[e0 & 63u];
+                    const u32 l1 = lrow[e1 & 63u];
+                    if (l0 != 0xFFu) *st++ = ((e0 & 0xFFC0u) << 9) + (l0 << 5) + pj;
+                    if (p + 2 < pe && l1 != 0xFFu) *st++ = ((e1 & 0xFFC0u) << 9) + (l1 << 5) + pj;
+                    p += 4;
+                }
+#else
                 while (true) {
                     if (p == pe) {
                         if (++j == k) break;
@@ -539,10 +621,26 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                         continue;
                     }
                     const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
+#if EMIT_ALU_LMAP
+                    const u32 x = e & 63u;
+                    if ((((x & 32u) ? Shi : Slo) >> (x & 31u)) & 1u) {
+                        const u32 pat = x * 0x01010101u;
+                        const u32 m0 = __vcmpeq4(nb4[0], pat), m1 = __vcmpeq4(nb4[1], pat);
+                        u32 l;
+                        if (m0 | m1) l = m0 ? ((u32)(__ffs(m0) - 1) >> 3) : 4u + ((u32)(__ffs(m1) - 1) >> 3);
+                        else {
+                            const u32 m2 = __vcmpeq4(nb4[2], pat), m3 = __vcmpeq4(nb4[3], pat);
+                            l = m2 ? 8u + ((u32)(__ffs(m2) - 1) >> 3) : 12u + ((u32)(__ffs(m3) - 1) >> 3);
+                        }
+                        *st++ = ((e & 0xFFC0u) << 9) + (l << 5) + pj;
+                    }
+#else
                     const u32 l = lrow[e & 63u];
                     if (l != 0xFFu) *st++ = ((e & 0xFFC0u) << 9) + (l << 5) + pj;
+#endif
                     p += 2;
                 }
+#endif
             }
             __syncwarp();
             // ---- flush: entry e of the run goes to global position base + e ------------------------------
@@ -733,8 +831,19 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
     small_items(m, &tpi, &ipg);
     {
         const int64_t items = G * ipg;
-        k_sample_small<<<(unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS), SAMP_WARPS * 32, 0, st>>>(
-            ptr, G, node_base, m, k, seed, graph_index_base, tpi, ipg, w, nodes, edge_ptr, sample_ptr);
+        const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
+#define UGS_LAUNCH_SAMPLE(KT_)                                                                                   \
+    k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, tpi, \
+                                                            ipg, w, nodes, edge_ptr, sample_ptr)
+        switch (k) {
+            case 3: UGS_LAUNCH_SAMPLE(3); break;
+            case 4: UGS_LAUNCH_SAMPLE(4); break;
+            case 5: UGS_LAUNCH_SAMPLE(5); break;
+            case 6: UGS_LAUNCH_SAMPLE(6); break;
+            case 8: UGS_LAUNCH_SAMPLE(8); break;
+            default: UGS_LAUNCH_SAMPLE(0); break;
+        }
+#undef UGS_LAUNCH_SAMPLE
         UGS_LAUNCH_CHECK("k_sample_small");
     }
     if (n_general > 0) {
