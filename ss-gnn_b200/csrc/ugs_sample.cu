@@ -11,9 +11,6 @@
 #include "ugs_common.cuh"
 
 #define SAMP_WARPS 8
-#ifndef EMIT_WARPS
-#define EMIT_WARPS 8
-#endif
 
 // =====================================================================================================
 // Bitmask path: sample + count
@@ -411,47 +408,43 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 
 // =====================================================================================================
 // Bitmask path: emission. One thread walks the CSR rows of its sample (a single flattened loop over
-// (j, p), so lanes only wait for the longest sample, not the longest row), packs every hit into a 32-bit
-// staging word in shared memory at the sample's final offset, and the warp then flushes the staged run
-// with fully coalesced 8-byte stores (32 consecutive output entries per store instruction).
+// (j, p), so lanes only wait for the longest sample, not the longest row), packs every hit into a staging
+// word in shared memory at the sample's final offset, and the warp then flushes the staged run with fully
+// coalesced 8-byte stores (32 consecutive output entries per store instruction).
+// The kernel is bound by shared-memory latency per resident warp, and shared memory per warp bounds the
+// resident warps: for k <= 8 in mode "sample" a staged entry is 16 bits (payload:10 | l:3 | j:3), which
+// brings a warp to 7.0 KB and 32 warps per SM; other modes stage 32 bits (9.6 KB, 24 warps per SM).
+// (Tried and measured slower, see profiles/README.md: 8 lanes per CSR row with ballot compaction; membership
+// and local index from registers instead of lmap[]; two entries per walk step; per-lane node loads.)
 // =====================================================================================================
-#ifndef EMIT_STAGE
+#ifndef EMIT_WARPS
+#define EMIT_WARPS 8
+#endif
 #define EMIT_STAGE 1280  // staged entries per flush; a sample never has more than 768 (= 2 * max columns)
-#endif
-#ifndef EMIT_DIRECT_NODES
-#define EMIT_DIRECT_NODES 0
-#endif
-#ifndef EMIT_UNROLLED_FLUSH
-#define EMIT_UNROLLED_FLUSH 1
-#endif
-#ifndef EMIT_MIN_BLOCKS
-#define EMIT_MIN_BLOCKS 3
-#endif
-#ifndef EMIT_PAIRWALK
-#define EMIT_PAIRWALK 0  // (measured slower) rows padded to an even number of entries; the walk handles two entries per step
-#endif
-#ifndef EMIT_ALU_LMAP
-#define EMIT_ALU_LMAP 0  // 1: membership + local index from registers (bit test + byte compare) instead of lmap[]
-#endif
 #define LMAP_STRIDE 68   // 17 words: the 32 per-sample rows start in 32 different banks
 
+template <typename StageT>
 struct __align__(16) SmallEmit {
-    u32 stage[EMIT_STAGE];                  // payload << 15 | sample lane << 10 | l << 5 | j
+    StageT stage[EMIT_STAGE];
     u32 rowrange[64];                       // byte offsets into ent[]: 2*rowptr[v] | 2*rowptr[v+1] << 16
-    unsigned char tile[32][16];             // node rows as local ids (mode "global" only)
+    unsigned char tile[32][16];             // node rows as local ids, 0xFF = -1
     unsigned char lmap[32][LMAP_STRIDE];    // local vertex id -> position inside its sample, 0xFF = not a member
-    unsigned short ent[2 * UGS_SMALL_MAX_COLS + (EMIT_PAIRWALK ? 64 : 0)];  // CSR entry: neighbour id | payload << 6
+    unsigned short ent[2 * UGS_SMALL_MAX_COLS];  // CSR entry: neighbour id | payload << 6
 };
 // payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
 // when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
 
-__global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS)
+// NARROW: k <= 8 and mode "sample": staged entry = payload << 6 | l << 3 | j          (16 bits)
+// else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
+template <bool NARROW>
+__global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? 4 : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
-             const i64* __restrict__ edge_ptr, i64 total, i64* __restrict__ out_u, i64* __restrict__ out_v,
+             const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
              i64* __restrict__ out_src) {
+    typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
-    SmallEmit* sm_all = reinterpret_cast<SmallEmit*>(emit_smem_raw);
+    SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
     const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
@@ -469,48 +462,24 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 sA = g * m + (i64)t0 * 32, sB = min(g * m + m, g * m + (i64)t1 * 32);
         if (edge_ptr[sA] == edge_ptr[sB]) return;
     }
-    SmallEmit& s = sm_all[warp];
+    SmallEmit<stage_t>& s = sm_all[warp];
     const i64 c0 = w.cstart[g];
     const i32* __restrict__ gcol = w.csr_col + 2 * c0;
     {
         const u32* rp = w.rowptr + nb + g;
         const i32* ci = w.csr_idx + 2 * c0;
-#if EMIT_PAIRWALK
-        // pad every row to an even number of entries so that a row starts on a 4-byte boundary
-        const u32 lt = (1u << lane) - 1u;
-        const u32 r0 = (lane < n) ? rp[lane] : 0, r0e = (lane < n) ? rp[lane + 1] : 0;
-        const u32 r1 = (lane + 32 < n) ? rp[lane + 32] : 0, r1e = (lane + 32 < n) ? rp[lane + 33] : 0;
-        const u32 b0 = __ballot_sync(FULL_MASK, (r0e - r0) & 1u), b1 = __ballot_sync(FULL_MASK, (r1e - r1) & 1u);
-        const u32 ps0 = r0 + __popc(b0 & lt), ps1 = r1 + __popc(b0) + __popc(b1 & lt);
-        if (lane < n) {
-            s.rowrange[lane] = (ps0 << 1) | ((ps0 + (r0e - r0)) << 17);
-            for (u32 q = 0; q < r0e - r0; ++q) {
-                const u32 pp = r0 + q;
-                const u32 payload = use_perm ? pp : (u32)(gcol[pp] - (i32)c0);
-                s.ent[ps0 + q] = (unsigned short)((u32)ci[pp] | (payload << 6));
-            }
-        }
-        if (lane + 32 < n) {
-            s.rowrange[lane + 32] = (ps1 << 1) | ((ps1 + (r1e - r1)) << 17);
-            for (u32 q = 0; q < r1e - r1; ++q) {
-                const u32 pp = r1 + q;
-                const u32 payload = use_perm ? pp : (u32)(gcol[pp] - (i32)c0);
-                s.ent[ps1 + q] = (unsigned short)((u32)ci[pp] | (payload << 6));
-            }
-        }
-#else
         for (int v = lane; v < n; v += 32) s.rowrange[v] = (rp[v] << 1) | (rp[v + 1] << 17);
         for (int p = lane; p < gi.nnz; p += 32) {
             const u32 payload = use_perm ? (u32)p : (u32)(gcol[p] - (i32)c0);
             s.ent[p] = (unsigned short)((u32)ci[p] | (payload << 6));
         }
-#endif
         u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
 #pragma unroll
         for (int q = 0; q < LMAP_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
     }
     unsigned char* lrow = &s.lmap[lane][0];
     const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent);
+    const int r32 = 32 % k, q32 = 32 / k;
 
     for (int t = t0; t < t1; ++t) {
         const i64 s0 = g * m + (i64)t * 32;
@@ -520,28 +489,9 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 tile_end = edge_ptr[s0 + nv];
         const i64 my_hi = __shfl_down_sync(FULL_MASK, my_lo, 1);
         const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
-        if (tile_end == __shfl_sync(FULL_MASK, my_lo, 0)) continue;
-        // per-sample state of the owning lane: node bytes in registers + local-index map (= membership test).
-        // Rows with a -1 have no entries (sampler.cpp:220-223), so only rows with entries are read.
-        u32 nb4[4] = {~0u, ~0u, ~0u, ~0u};
-        const bool walk = (lane < nv) && (my_end > my_lo);
-#if EMIT_DIRECT_NODES
-        if (walk) {
-            const i64* in = nodes + (s0 + lane) * k;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (j < k) {
-                    const u32 v = (u32)(in[j] - lo) & 0xFFu;
-                    nb4[j >> 2] = (nb4[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (v << (8 * (j & 3)));
-                    lrow[v] = (unsigned char)j;
-                }
-            }
-            if (mode == UGS_MODE_GLOBAL)
-                *reinterpret_cast<uint4*>(&s.tile[lane][0]) = make_uint4(nb4[0], nb4[1], nb4[2], nb4[3]);
-        }
-#else
+        const i64 tile_lo = __shfl_sync(FULL_MASK, my_lo, 0);
+        if (tile_end == tile_lo) continue;
         {   // node rows -> shared tile (coalesced read)
-            const int r32 = 32 % k, q32 = 32 / k;
             int sidx = lane / k, j = lane - sidx * k;
             const i64* in = nodes + s0 * k;
             for (int e = lane; e < nv * k; e += 32) {
@@ -552,6 +502,10 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
             }
         }
         __syncwarp();
+        // per-sample state of the owning lane: node bytes in registers + local-index map (= membership test).
+        // Rows with a -1 have no entries (sampler.cpp:220-223), so only rows with entries are walked.
+        u32 nb4[4] = {~0u, ~0u, ~0u, ~0u};
+        const bool walk = (lane < nv) && (my_end > my_lo);
         if (walk) {
             const uint4 nn = *reinterpret_cast<const uint4*>(&s.tile[lane][0]);
             nb4[0] = nn.x; nb4[1] = nn.y; nb4[2] = nn.z; nb4[3] = nn.w;
@@ -559,23 +513,10 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
             for (int j = 0; j < 16; ++j)
                 if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)j;
         }
-#endif
-#if EMIT_ALU_LMAP
-        u32 Slo = 0, Shi = 0;
-        if (walk) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < k) {
-                    const u32 v = (nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    if (v & 32u) Shi |= 1u << (v & 31u); else Slo |= 1u << v;
-                }
-        }
-#endif
         // balanced sub-batches: when the tile does not fit the staging buffer, aim for equal shares
-        const int tile_total = (int)min(tile_end - __shfl_sync(FULL_MASK, my_lo, 0), (i64)0x7fffffff);
+        const int tile_total = (int)min(tile_end - tile_lo, (i64)0x7fffffff);
         const int nsplit = (tile_total + EMIT_STAGE - 1) / EMIT_STAGE;
         const int cap_eff = (nsplit <= 1) ? EMIT_STAGE : min(EMIT_STAGE, tile_total / nsplit + 48);
-        // sub-batches of consecutive samples whose entries fit the staging buffer
         int sa = 0;
         while (sa < nv) {
             const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
@@ -585,85 +526,53 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
             if (sb == sa) sb = sa + 1;  // a single sample always fits EMIT_STAGE (<= 768 entries)
             const int run = (int)(((sb == nv) ? tile_end : __shfl_sync(FULL_MASK, my_lo, sb & 31)) - base);
             if (walk && lane >= sa && lane < sb) {
-                u32* st = s.stage + (int)(my_lo - base);
-                u32 pj = (u32)lane << 10;  // | j
+                stage_t* st = s.stage + (int)(my_lo - base);
+                u32 pj = NARROW ? 0u : ((u32)lane << 10);  // | j
                 int j = 0;
                 u32 rr = s.rowrange[nb4[0] & 0xFFu];
                 u32 p = rr & 0xFFFFu, pe = rr >> 16;  // byte offsets into ent[]
-#if EMIT_PAIRWALK && !EMIT_ALU_LMAP
-                while (true) {
-                    bool done = false;
-                    while (p >= pe) {
-                        if (++j == k) { done = true; break; }
-                        const u32 wsel = (j < 4) ? nb4[0] : (j < 8) ? nb4[1] : (j < 12) ? nb4[2] : nb4[3];
-                        rr = s.rowrange[(wsel >> (8 * (j & 3))) & 0xFFu];
-                        p = rr & 0xFFFFu; pe = rr >> 16;
-                        pj++;
-                    }
-                    if (done) break;
-                    const u32 two = *reinterpret_cast<const u32*>(entb + p);  // rows start 4-byte aligned
-                    const u32 e0 = two & 0xFFFFu, e1 = two >> 16;
-                    const u32 l0 = lrow[e0 & 63u];
-                    const u32 l1 = lrow[e1 & 63u];
-                    if (l0 != 0xFFu) *st++ = ((e0 & 0xFFC0u) << 9) + (l0 << 5) + pj;
-                    if (p + 2 < pe && l1 != 0xFFu) *st++ = ((e1 & 0xFFC0u) << 9) + (l1 << 5) + pj;
-                    p += 4;
-                }
-#else
                 while (true) {
                     if (p == pe) {
                         if (++j == k) break;
                         const u32 wsel = (j < 4) ? nb4[0] : (j < 8) ? nb4[1] : (j < 12) ? nb4[2] : nb4[3];
-                        const u32 v = (wsel >> (8 * (j & 3))) & 0xFFu;
-                        rr = s.rowrange[v];
+                        rr = s.rowrange[(wsel >> (8 * (j & 3))) & 0xFFu];
                         p = rr & 0xFFFFu; pe = rr >> 16;
                         pj++;
                         continue;
                     }
                     const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
-#if EMIT_ALU_LMAP
-                    const u32 x = e & 63u;
-                    if ((((x & 32u) ? Shi : Slo) >> (x & 31u)) & 1u) {
-                        const u32 pat = x * 0x01010101u;
-                        const u32 m0 = __vcmpeq4(nb4[0], pat), m1 = __vcmpeq4(nb4[1], pat);
-                        u32 l;
-                        if (m0 | m1) l = m0 ? ((u32)(__ffs(m0) - 1) >> 3) : 4u + ((u32)(__ffs(m1) - 1) >> 3);
-                        else {
-                            const u32 m2 = __vcmpeq4(nb4[2], pat), m3 = __vcmpeq4(nb4[3], pat);
-                            l = m2 ? 8u + ((u32)(__ffs(m2) - 1) >> 3) : 12u + ((u32)(__ffs(m3) - 1) >> 3);
-                        }
-                        *st++ = ((e & 0xFFC0u) << 9) + (l << 5) + pj;
-                    }
-#else
                     const u32 l = lrow[e & 63u];
-                    if (l != 0xFFu) *st++ = ((e & 0xFFC0u) << 9) + (l << 5) + pj;
-#endif
+                    if (l != 0xFFu) {
+                        if (NARROW) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
+                        else *st++ = (stage_t)(((e & 0xFFC0u) << 9) + (l << 5) + pj);
+                    }
                     p += 2;
                 }
-#endif
             }
             __syncwarp();
             // ---- flush: entry e of the run goes to global position base + e ------------------------------
-            if (EMIT_UNROLLED_FLUSH && mode == UGS_MODE_SAMPLE && !use_perm) {
+            if (NARROW) {
                 i64* pu = out_u + base + lane;
                 i64* pv = out_v + base + lane;
                 i64* ps = out_src + base + lane;
-                const u32* sg = s.stage + lane;
+                const stage_t* sg = s.stage + lane;
                 int e = lane;
-                for (; e + 96 < run; e += 128) {  // four full warp-rows per trip, no bounds checks
-                    const u32 k0_ = sg[0], k1_ = sg[32], k2_ = sg[64], k3_ = sg[96];
-                    pu[0] = (i64)(k0_ & 31u); pu[32] = (i64)(k1_ & 31u); pu[64] = (i64)(k2_ & 31u); pu[96] = (i64)(k3_ & 31u);
-                    pv[0] = (i64)((k0_ >> 5) & 31u); pv[32] = (i64)((k1_ >> 5) & 31u);
-                    pv[64] = (i64)((k2_ >> 5) & 31u); pv[96] = (i64)((k3_ >> 5) & 31u);
-                    ps[0] = c0 + (i64)(k0_ >> 15); ps[32] = c0 + (i64)(k1_ >> 15);
-                    ps[64] = c0 + (i64)(k2_ >> 15); ps[96] = c0 + (i64)(k3_ >> 15);
-                    pu += 128; pv += 128; ps += 128; sg += 128;
+                if (!use_perm) {
+                    for (; e + 96 < run; e += 128) {  // four full warp-rows per trip, no bounds checks
+                        const u32 k0_ = sg[0], k1_ = sg[32], k2_ = sg[64], k3_ = sg[96];
+                        pu[0] = (i64)(k0_ & 7u); pu[32] = (i64)(k1_ & 7u); pu[64] = (i64)(k2_ & 7u); pu[96] = (i64)(k3_ & 7u);
+                        pv[0] = (i64)((k0_ >> 3) & 7u); pv[32] = (i64)((k1_ >> 3) & 7u);
+                        pv[64] = (i64)((k2_ >> 3) & 7u); pv[96] = (i64)((k3_ >> 3) & 7u);
+                        ps[0] = c0 + (i64)(k0_ >> 6); ps[32] = c0 + (i64)(k1_ >> 6);
+                        ps[64] = c0 + (i64)(k2_ >> 6); ps[96] = c0 + (i64)(k3_ >> 6);
+                        pu += 128; pv += 128; ps += 128; sg += 128;
+                    }
                 }
                 for (; e < run; e += 32) {
                     const u32 pk = sg[0];
-                    pu[0] = (i64)(pk & 31u);
-                    pv[0] = (i64)((pk >> 5) & 31u);
-                    ps[0] = c0 + (i64)(pk >> 15);
+                    pu[0] = (i64)(pk & 7u);
+                    pv[0] = (i64)((pk >> 3) & 7u);
+                    ps[0] = use_perm ? (i64)__ldg(gcol + (pk >> 6)) : c0 + (i64)(pk >> 6);
                     pu += 32; pv += 32; ps += 32; sg += 32;
                 }
             } else {
@@ -695,7 +604,6 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                 if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)0xFF;
         }
     }
-    (void)total;
 }
 
 // =====================================================================================================
@@ -906,10 +814,18 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
         int tpi; int64_t ipg;
         small_items(m, &tpi, &ipg);
         const int64_t items = G * ipg;
-        const size_t smem = sizeof(SmallEmit) * EMIT_WARPS;
-        UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_emit_small<<<(unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS), EMIT_WARPS * 32, smem, st>>>(
-            ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w, nodes, edge_ptr, total, out_u, out_v, edge_src_out);
+        const unsigned grid = (unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS);
+        if (k <= 8 && mode == UGS_MODE_SAMPLE) {
+            const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
+                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out);
+        } else {
+            const size_t smem = sizeof(SmallEmit<u32>) * EMIT_WARPS;
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_emit_small<false><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
+                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out);
+        }
         UGS_LAUNCH_CHECK("k_emit_small");
     }
     if (n_general > 0) {
