@@ -269,13 +269,14 @@ def main():
         last.update(stats=stats, total=total, n_general=b.n_general)
         return e0.elapsed_time(e3)
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()  # sampled from the warm-up to the end of the e2e leg (the timed regions are milliseconds long)
     for w in range(args.warmup):
         step(100 + w, False)
     launches0 = int(L.ugs_launch_count())
     barrier()
-    with ClockSampler(local_rank) as clk:
-        times = [step(1000 + s, True) for s in range(args.steps)]
-        barrier()
+    times = [step(1000 + s, True) for s in range(args.steps)]
+    barrier()
     launches = int(L.ugs_launch_count()) - launches0
     t_local = sum(times) / 1e3
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
@@ -342,6 +343,7 @@ def main():
                "steps": args.e2e_steps, "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu tensors"}
         del outs
 
+    clk.__exit__(None, None, None)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = os.cpu_count() or 1

@@ -337,6 +337,9 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ scratch,
               unsigned long long* __restrict__ counters) {
+    // Coalesced global access (a warp reads 32 consecutive counts per instruction), transposed through a padded
+    // shared tile so that every thread scans SCAN_ITEMS consecutive counts in registers.
+    __shared__ i64 s_tile_[SCAN_THREADS / 32][32 * (SCAN_ITEMS + 1)];
     __shared__ i64 s_warp[SCAN_THREADS / 32];
     __shared__ i64 s_prefix;
     __shared__ unsigned int s_tile;
@@ -345,15 +348,23 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
     if (threadIdx.x == 0) s_tile = (unsigned int)atomicAdd(ticket, 1ull);
     __syncthreads();
     const i64 tile = s_tile;
-    const i64 base = tile * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    i64* st = s_tile_[warp];
+    const i64 wbase = tile * SCAN_TILE + (i64)warp * (32 * SCAN_ITEMS);  // this warp's 512 consecutive counts
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+        const int it = q * 32 + lane;  // item index inside the warp chunk
+        const i64 gi_ = wbase + it;
+        st[(it / SCAN_ITEMS) * (SCAN_ITEMS + 1) + (it % SCAN_ITEMS)] = (gi_ < B) ? data[gi_] : 0;
+    }
+    __syncwarp();
     i64 v[SCAN_ITEMS];
     i64 local = 0;
 #pragma unroll
     for (int q = 0; q < SCAN_ITEMS; ++q) {
-        v[q] = (base + q < B) ? data[base + q] : 0;
+        v[q] = st[lane * (SCAN_ITEMS + 1) + q];
         local += v[q];
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     i64 incl = local;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -402,7 +413,14 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 #pragma unroll
     for (int q = 0; q < SCAN_ITEMS; ++q) {
         run += v[q];
-        if (base + q < B) data[base + q] = run;
+        st[lane * (SCAN_ITEMS + 1) + q] = run;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+        const int it = q * 32 + lane;
+        const i64 gi_ = wbase + it;
+        if (gi_ < B) data[gi_] = st[(it / SCAN_ITEMS) * (SCAN_ITEMS + 1) + (it % SCAN_ITEMS)];
     }
 }
 
