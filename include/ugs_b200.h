@@ -182,6 +182,24 @@ int ugs_eps_emit_edges(const int64_t* edge_index, int64_t E, const int64_t* ptr,
                        const ugs_layout* L, const int64_t* nodes, const int64_t* edge_ptr, int64_t total,
                        int64_t* edge_index_out, int64_t* edge_src_out, void* stream);
 
+/* ---- APX-UGS (reference src/samplers/apx_ugs_sampler/src/apx_ugs_sampler.cpp) -----------------
+ * One graph per call, like the reference: the columns [e0, e1) of edge_index (the reference reads `ptr` as an EDGE
+ * range, :15-33), n = max vertex id + 1 <= 1024, 2 <= k <= 8.
+ *   ugs_apx_prepare  Graph::Graph + apx_dd (:10-169). Syncs; h_info = {n, adjacency entries, Z > 0}.
+ *   ugs_apx_trials   one round: trials [tbase, tbase+per_sample) of every sample, one warp per (sample, trial);
+ *                    h_best[s] = first accepted trial so far (>= 10^6: none). Syncs. The caller loops rounds until
+ *                    every sample has best[s] < tbase + per_sample or tbase reaches max_trials (10^6, :411).
+ *   ugs_apx_write    samples[k, n_ok] (row-major, :508-515); slot[s] = output column of sample s or -1 (dropped). */
+size_t ugs_apx_workspace_bytes(int64_t n_columns, int64_t m);
+int ugs_apx_prepare(const int64_t* edge_index, int64_t E, int64_t e0, int64_t e1, int64_t m, int k, uint64_t seed,
+                    double epsilon, void* workspace, size_t ws_bytes, int64_t* h_info, void* stream);
+int ugs_apx_trials(int n, int64_t n_columns, int64_t m, int k, uint64_t seed, double epsilon, int tbase,
+                   int per_sample, int max_trials, void* workspace, int32_t* h_best, void* stream);
+int ugs_apx_write(int n, int64_t n_columns, int64_t m, int k, uint64_t seed, double epsilon, const int32_t* slot,
+                  int n_ok, void* workspace, int64_t* samples_out, void* stream);
+int ugs_apx_dump(int n, int64_t nnz, int64_t n_columns, int64_t m, void* workspace, int32_t* rowptr, int32_t* adj,
+                 int32_t* order, int32_t* position, double* est, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
