@@ -491,6 +491,28 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
                     }
                 }
                 if (lane < d) { ccol[p0 + lane] = (i32)(key >> 32); cidx[p0 + lane] = (i32)(u32)key; }
+            } else if (d <= 128) {
+                // medium row: this warp sorts it alone in its 1 KB slice of the sort buffer (4 keys per lane)
+                u64* wb = sbuf + warp * 128;
+                for (int i = lane; i < 128; i += 32)
+                    wb[i] = (i < d) ? ((((u64)(u32)ccol[p0 + i]) << 32) | (u32)cidx[p0 + i]) : ~0ull;
+                __syncwarp();
+                for (int k2 = 2; k2 <= 128; k2 <<= 1) {
+                    for (int j = k2 >> 1; j >= 1; j >>= 1) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int t = lane + 32 * q;  // 64 compare-exchanges per stage
+                            const int lo_ = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const int hi_ = lo_ | j;
+                            const bool up = ((lo_ & k2) == 0);
+                            const u64 a = wb[lo_], b = wb[hi_];
+                            if ((a > b) == up) { wb[lo_] = b; wb[hi_] = a; }
+                        }
+                        __syncwarp();
+                    }
+                }
+                for (int i = lane; i < d; i += 32) { ccol[p0 + i] = (i32)(wb[i] >> 32); cidx[p0 + i] = (i32)(u32)wb[i]; }
+                __syncwarp();
             } else if (lane == 0) {
                 sdg[atomicAdd(&s_cnt[0], 1)] = v;
             }
