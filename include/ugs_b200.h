@@ -56,6 +56,7 @@ extern "C" {
 #define UGS_MAX_K 32           /* general path; the bitmask fast path takes k <= 16 */
 #define UGS_SMALL_MAX_N 64     /* graphs with <= 64 nodes take the one-thread-per-sample bitmask path */
 #define UGS_SMALL_MAX_COLS 384 /* ... if they also have <= 384 edge columns */
+#define UGS_LARGE_N 4096       /* general-path graphs above this are preprocessed by the whole GPU, one at a time */
 
 /* Byte offsets of every array inside the caller-allocated preprocessing workspace. The arrays are the
  * device-resident equivalent of the reference's `struct Preproc` (sampler.hpp:81-93), stored once for the
@@ -78,6 +79,8 @@ typedef struct ugs_layout {
     size_t csr_idx;    /* int32  [2E]    neighbour local id                        (Preproc::indices)    */
     size_t csr_col;    /* int32  [2E]    batch-global source column                (edge_col_of_csr_pos -> g_edge2global) */
     size_t gaux;       /* double [G]     per-graph acceptance constant C of UGS_VARIANT_UNIFORM                  */
+    size_t llist;      /* int32  [G]     ids of the large general-path graphs (> UGS_LARGE_N nodes)              */
+    size_t lscratch;   /* double [4096]  scratch of the cooperative large-graph kernel                           */
 } ugs_layout;
 
 typedef struct ugs_ginfo {
@@ -101,6 +104,7 @@ typedef struct ugs_ginfo {
 #define UGS_CTR_RELAXED 6       /* graphs sampled at relaxation level > 0                                */
 #define UGS_CTR_TRIALS 7        /* growth attempts (== samples for VARIANT_REF)                          */
 #define UGS_CTR_SCAN_TICKET 8
+#define UGS_CTR_N_LARGE 9        /* general-path graphs with more than UGS_LARGE_N nodes                   */
 
 int ugs_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (monotonic; for measurement). */
@@ -122,14 +126,14 @@ int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout* out);
 int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int k,
                       int skip_lt_k, int fast, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream);
 
-/* Copies counters[0..7] to h_out (synchronises the stream). */
+/* Copies counters[0..15] to h_out (16 x int64; synchronises the stream). */
 int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
 
 /* A.2-A.5 -- per-graph CSR (multigraph, column order), (degree,id) order, suffix degrees, reachability,
  * bucket weights, root CDF. n_general / max_n_general come from ugs_batch_info. */
 int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
-                      int k, const int64_t* perm, int64_t n_general, void* workspace, const ugs_layout* L,
-                      void* stream);
+                      int k, const int64_t* perm, int64_t n_general, int64_t n_large, void* workspace,
+                      const ugs_layout* L, void* stream);
 
 /* Scratch bytes ugs_sample_batch needs for G*m samples. */
 size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);

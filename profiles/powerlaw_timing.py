@@ -1,5 +1,5 @@
 import sys, time
-sys.path.insert(0,'.'); sys.path.insert(0,'ss-gnn_b200')
+import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'ss-gnn_b200'))
 import numpy as np, torch
 from ugs_b200 import synth
 from ugs_b200.engine import DeviceBatch

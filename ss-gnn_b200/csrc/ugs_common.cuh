@@ -46,6 +46,8 @@ struct WS {
     i32* csr_idx;
     i32* csr_col;
     double* gaux;
+    i32* llist;        // ids of the LARGE general-path graphs (preprocessed by the cooperative kernel)
+    double* lscratch;  // [4096] scratch of the cooperative kernel
 };
 
 static inline WS ws_views(void* base, const ugs_layout* L) {
@@ -67,6 +69,8 @@ static inline WS ws_views(void* base, const ugs_layout* L) {
     w.csr_idx = (i32*)(b + L->csr_idx);
     w.csr_col = (i32*)(b + L->csr_col);
     w.gaux = (double*)(b + L->gaux);
+    w.llist = (i32*)(b + L->llist);
+    w.lscratch = (double*)(b + L->lscratch);
     return w;
 }
 

@@ -82,6 +82,7 @@ __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_l
         unsigned long long slot = atomicAdd(&w.counters[UGS_CTR_N_GENERAL], 1ull);
         w.glist[slot] = (i32)g;
         atomicMax(&w.counters[UGS_CTR_MAX_N_GENERAL], (unsigned long long)n);
+        if (n > UGS_LARGE_N) w.llist[atomicAdd(&w.counters[UGS_CTR_N_LARGE], 1ull)] = (i32)g;
     }
     w.ginfo[g] = gi;
 }
@@ -428,6 +429,7 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
         const i64 g = w.glist[item];
         const i64 lo = ptr[g];
         const int n = (int)(ptr[g + 1] - lo);
+        if (n > UGS_LARGE_N) continue;  // large graphs: k_preproc_large (whole GPU per graph)
         const i64 c0 = w.cstart[g];
         const i64 nc = w.cstart[g + 1] - c0;
         const i64 nb = lo - node_base;
@@ -728,6 +730,8 @@ extern "C" int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout
     L->csr_idx = take(sizeof(i32) * (size_t)(2 * E + 1));
     L->csr_col = take(sizeof(i32) * (size_t)(2 * E + 1));
     L->gaux = take(sizeof(double) * (size_t)(G + 1));
+    L->llist = take(sizeof(i32) * (size_t)(G + 1));
+    L->lscratch = take(sizeof(double) * 4096);
     L->total_bytes = off;
     return UGS_OK;
 }
@@ -763,14 +767,17 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
 extern "C" int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream_) {
     if (!workspace || !L || !h_out) return ugs_set_error(UGS_EINVAL, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream_;
-    UGS_CUDA_CHECK(cudaMemcpyAsync(h_out, (const char*)workspace + L->counters, sizeof(i64) * 8,
+    UGS_CUDA_CHECK(cudaMemcpyAsync(h_out, (const char*)workspace + L->counters, sizeof(i64) * 16,
                                    cudaMemcpyDeviceToHost, st));
     UGS_CUDA_CHECK(cudaStreamSynchronize(st));
     return UGS_OK;
 }
 
+int ugs_launch_preproc_large(const i64* row0, const i64* row1, const i64* ptr, i64 node_base, int k, const i64* perm,
+                             i64 n_large, WS& w, cudaStream_t st);  // ugs_preproc_large.cu
+
 extern "C" int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G,
-                                 int64_t node_base, int k, const int64_t* perm, int64_t n_general,
+                                 int64_t node_base, int k, const int64_t* perm, int64_t n_general, int64_t n_large,
                                  void* workspace, const ugs_layout* L, void* stream_) {
     if (!workspace || !L) return ugs_set_error(UGS_EINVAL, "NULL workspace/layout");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
@@ -785,7 +792,11 @@ extern "C" int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int
             row0, row1, ptr, G, node_base, k, perm, w);
         UGS_LAUNCH_CHECK("k_preproc_small");
     }
-    if (n_general > 0) {
+    if (n_large > 0) {
+        const int rc = ugs_launch_preproc_large(row0, row1, ptr, node_base, k, perm, n_large, w, st);
+        if (rc != UGS_OK) return rc;
+    }
+    if (n_general > n_large) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

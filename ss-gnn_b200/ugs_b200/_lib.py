@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -28,7 +28,7 @@ class LibraryMissing(RuntimeError):
 class Layout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "total_bytes", "cstart", "ginfo", "glist", "counters", "colkey", "rowptr", "order", "index_of",
-        "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col", "gaux")]
+        "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col", "gaux", "llist", "lscratch")]
 
 
 def nvcc_command(out: str = SO):
@@ -68,7 +68,7 @@ def lib():
     L.ugs_workspace_layout.argtypes = [i64, i64, i64, LP]
     L.ugs_segment_batch.argtypes = [vp, i64, vp, i64, ci, ci, ci, vp, vp, LP, vp]
     L.ugs_batch_info.argtypes = [vp, LP, vp, vp]
-    L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, vp, LP, vp]
+    L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, vp, LP, vp]
     L.ugs_sample_scratch_bytes.restype = sz
     L.ugs_sample_scratch_bytes.argtypes = [i64, i64]
     L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]

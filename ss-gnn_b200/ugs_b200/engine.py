@@ -13,7 +13,8 @@ from . import _lib
 
 MODES = {"sample": 0, "graph": 1, "global": 2}
 VARIANTS = {"ref": 0, "uniform": 1}
-CTR = dict(unsorted=0, n_general=1, max_n_general=2, n_skipped=3, total_edges=4, incomplete=5, relaxed=6, trials=7)
+CTR = dict(unsorted=0, n_general=1, max_n_general=2, n_skipped=3, total_edges=4, incomplete=5, relaxed=6, trials=7,
+           n_large=9)
 
 
 def _ptr(t):
@@ -56,7 +57,7 @@ class DeviceBatch:
         _lib.check(L.ugs_workspace_layout(self.E, max(self.G, 0), self.NT, ctypes.byref(self.layout)))
         self.ws = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
         self.perm = None
-        self._info_host = torch.empty(8, dtype=torch.int64).pin_memory()
+        self._info_host = torch.empty(16, dtype=torch.int64).pin_memory()
         self._skip_lt_k = skip_lt_k
         self.variant = variant
         if variant not in ("ref", "uniform"):
@@ -88,8 +89,9 @@ class DeviceBatch:
             self.n_general = int(info[CTR["n_general"]])
             self.max_n_general = int(info[CTR["max_n_general"]])
             self.n_skipped = int(info[CTR["n_skipped"]])
+            self.n_large = int(info[CTR["n_large"]])
             _lib.check(L.ugs_preproc_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.node_base,
-                                           self.k, _ptr(self.perm), self.n_general, _ptr(self.ws),
+                                           self.k, _ptr(self.perm), self.n_general, self.n_large, _ptr(self.ws),
                                            ctypes.byref(self.layout), _stream()))
             if self.variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
                 _lib.check(L.ugs_preproc_uniform(_ptr(self.ptr), self.G, self.node_base, self.k, self.n_general,
@@ -110,7 +112,7 @@ class DeviceBatch:
                                                 ctypes.byref(self.layout), _stream()))
 
     def info(self):
-        """counters[0..7] as a list of python ints (synchronises the current stream)."""
+        """counters[0..15] as a list of python ints (synchronises the current stream)."""
         _lib.check(_lib.lib().ugs_batch_info(_ptr(self.ws), ctypes.byref(self.layout),
                                              ctypes.c_void_p(self._info_host.data_ptr()), _stream()))
         return [int(x) for x in self._info_host.tolist()]

@@ -217,3 +217,23 @@ def test_unsorted_columns_detected_late_by_sample(cuda_lib):
         ref = _oracle_batch(ei2, ptr, m, k, "global", 2)
         for x, r in zip(outs, ref):
             assert np.array_equal(x.cpu().numpy(), r)
+
+
+@pytest.mark.parametrize("k", [3, 6])
+def test_preproc_large_graphs_cooperative_kernel(cuda_lib, k):
+    """Graphs above UGS_LARGE_N = 4096 nodes are preprocessed by the whole GPU (cooperative kernel): a Barabasi-
+    Albert graph with hubs (rows far longer than a warp / the CTA sort buffer), a large random multigraph with
+    self loops and dropped columns, and small graphs in the same batch."""
+    from ugs_b200 import synth
+    rng = np.random.default_rng(41)
+    ba, pba = synth.barabasi_albert(6000, 3, seed=2)
+    star = bidir([(0, i) for i in range(1, 5000)] + [(i, i + 1) for i in range(1, 300)])  # hub row of 9998 entries
+    wei, wptr = random_batch(rng, 4, 5, 30, deg=2.0, big=[(1, 5000)])
+    ei, ptr = synth.concat_batches([(ba, pba), (star, np.array([0, 5000])), (wei, wptr)])
+    b = _batch(ei, ptr, k)
+    assert b.n_large == 3 and b.n_general >= 3
+    _check_tables(b, ei, ptr, k)
+    outs, _ = b.sample(50, k, "sample", seed=4)
+    ref = _oracle_batch(ei, ptr, 50, k, "sample", 4)
+    for a, r in zip(outs, ref):
+        assert np.array_equal(a.cpu().numpy(), r)
