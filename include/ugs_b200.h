@@ -126,6 +126,12 @@ int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout* out);
 int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int k,
                       int skip_lt_k, int fast, const int64_t* perm, void* workspace, const ugs_layout* L, void* stream);
 
+/* Slow path of A.1 (columns not grouped by graph; never a PyG batch): perm_out[E] = stable ordering of the columns
+ * by the graph ids ugs_segment_batch(fast = 0) left in the workspace (LSD radix sort). */
+size_t ugs_sort_scratch_bytes(int64_t E);
+int ugs_sort_columns(int64_t E, int64_t G, void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
+                     int64_t* perm_out, void* stream);
+
 /* Copies counters[0..15] to h_out (16 x int64; synchronises the stream). */
 int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
 

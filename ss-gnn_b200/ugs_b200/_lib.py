@@ -10,14 +10,14 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
     "ugs_abi_version", "ugs_launch_count", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
     "ugs_preproc_batch", "ugs_sample_scratch_bytes", "ugs_sample_batch", "ugs_emit_edges", "ugs_count_edges",
     "ugs_eps_sample_batch", "ugs_eps_emit_edges", "ugs_preproc_uniform",
-    "ugs_apx_workspace_bytes", "ugs_apx_prepare", "ugs_apx_trials", "ugs_apx_write", "ugs_apx_dump",
+    "ugs_sort_scratch_bytes", "ugs_sort_columns", "ugs_apx_workspace_bytes", "ugs_apx_prepare", "ugs_apx_trials", "ugs_apx_write", "ugs_apx_dump",
 ]
 
 
@@ -81,6 +81,9 @@ def lib():
     L.ugs_apx_trials.argtypes = [ci, i64, i64, ci, u64, cd, ci, ci, ci, vp, vp, vp]
     L.ugs_apx_write.argtypes = [ci, i64, i64, ci, u64, cd, vp, ci, vp, vp, vp]
     L.ugs_apx_dump.argtypes = [ci, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.ugs_sort_scratch_bytes.restype = sz
+    L.ugs_sort_scratch_bytes.argtypes = [i64]
+    L.ugs_sort_columns.argtypes = [i64, i64, vp, LP, vp, sz, vp, vp]
     L.ugs_preproc_uniform.argtypes = [vp, i64, i64, ci, i64, vp, LP, vp]
     L.ugs_eps_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ctypes.c_double, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_eps_emit_edges.argtypes = [vp, i64, vp, i64, i64, i64, ci, ci, vp, i64, vp, LP, vp, vp, i64, vp, vp, vp]

@@ -82,8 +82,12 @@ class DeviceBatch:
             if info[CTR["unsorted"]] & 1:
                 # Columns are not graph-contiguous (never the case for PyG batches): order them stably by
                 # graph id once and read them through `perm` from here on.
-                colkey = self.view("colkey")
-                self.perm = torch.sort(colkey, stable=True).indices.contiguous()
+                sb = int(L.ugs_sort_scratch_bytes(self.E))
+                scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
+                self.perm = torch.empty(self.E, dtype=torch.int64, device=self.device)
+                _lib.check(L.ugs_sort_columns(self.E, self.G, _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch),
+                                              sb, _ptr(self.perm), _stream()))
+                del scratch
                 self._segment(False)
                 info = self.info()
             self.n_general = int(info[CTR["n_general"]])

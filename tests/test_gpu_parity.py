@@ -237,3 +237,21 @@ def test_preproc_large_graphs_cooperative_kernel(cuda_lib, k):
     ref = _oracle_batch(ei, ptr, 50, k, "sample", 4)
     for a, r in zip(outs, ref):
         assert np.array_equal(a.cpu().numpy(), r)
+
+
+def test_column_sort_is_stable_on_many_graphs(cuda_lib):
+    """The slow path's LSD radix sort (several 8-bit passes: > 256 graphs, > 4096 columns per CTA tile)."""
+    rng = np.random.default_rng(23)
+    ei, ptr = random_batch(rng, 700, 2, 12, deg=2.0, weird=False)
+    perm = rng.permutation(ei.shape[1])
+    ei2 = np.ascontiguousarray(ei[:, perm])
+    b = _batch(ei2, ptr, 3)
+    b.ginfo()
+    assert b.perm is not None
+    gid = np.searchsorted(ptr, ei2[0], side="right") - 1
+    want = np.argsort(gid, kind="stable")
+    assert np.array_equal(b.perm.cpu().numpy(), want)
+    outs, _ = b.sample(4, 3, "sample", seed=6)
+    ref = _oracle_batch(ei2, ptr, 4, 3, "sample", 6)
+    for a, r in zip(outs, ref):
+        assert np.array_equal(a.cpu().numpy(), r)
