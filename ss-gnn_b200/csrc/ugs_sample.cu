@@ -549,6 +549,9 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                 int j = 0;
                 u32 rr = s.rowrange[nb4[0] & 0xFFu];
                 u32 p = rr & 0xFFFFu, pe = rr >> 16;  // byte offsets into ent[]
+                // One loop, two guarded blocks per trip (switch row / take one entry): lanes re-converge every trip,
+                // so a warp runs max_lane(entries of its sample) trips, not sum_j max_lane(row length).
+#pragma nounroll
                 while (true) {
                     if (p == pe) {
                         if (++j == k) break;
@@ -556,15 +559,17 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                         rr = s.rowrange[(wsel >> (8 * (j & 3))) & 0xFFu];
                         p = rr & 0xFFFFu; pe = rr >> 16;
                         pj++;
-                        continue;
                     }
-                    const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
-                    const u32 l = lrow[e & 63u];
-                    if (l != 0xFFu) {
-                        if (NARROW) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
-                        else *st++ = (stage_t)(((e & 0xFFC0u) << 9) + (l << 5) + pj);
+                    asm volatile("" ::: "memory");  // keep the two blocks in one loop (no loop nesting by the compiler)
+                    if (p != pe) {
+                        const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
+                        const u32 l = lrow[e & 63u];
+                        if (l != 0xFFu) {
+                            if (NARROW) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
+                            else *st++ = (stage_t)(((e & 0xFFC0u) << 9) + (l << 5) + pj);
+                        }
+                        p += 2;
                     }
-                    p += 2;
                 }
             }
             __syncwarp();
