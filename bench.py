@@ -270,7 +270,8 @@ def main():
         return e0.elapsed_time(e3)
 
     clk = ClockSampler(local_rank)
-    clk.__enter__()  # sampled from the warm-up to the end of the e2e leg (the timed regions are milliseconds long)
+    if rank == 0:  # one sampler per job: nvidia-smi takes a driver lock, N of them perturb the other ranks' launches
+        clk.__enter__()  # sampled from the warm-up to the end of the e2e leg (the timed regions are milliseconds long)
     for w in range(args.warmup):
         step(100 + w, False)
     launches0 = int(L.ugs_launch_count())
@@ -283,6 +284,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_max = float(t.item())
+    per_rank_ms = [1e3 * t_local / args.steps]
+    if world > 1:
+        tl = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        tg = [torch.empty_like(tl) for _ in range(world)]
+        dist.all_gather(tg, tl)
+        per_rank_ms = [1e3 * float(x.item()) / args.steps for x in tg]
 
     # the one collective of the design: all-gather of per-rank counts/statistics (never on the sampling path)
     st = last["stats"]
@@ -343,7 +350,8 @@ def main():
                "steps": args.e2e_steps, "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu tensors"}
         del outs
 
-    clk.__exit__(None, None, None)
+    if rank == 0:
+        clk.__exit__(None, None, None)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = os.cpu_count() or 1
@@ -367,6 +375,7 @@ def main():
                 "sharding": f"dp{world} by graph, no data-path collective",
             },
             "stage_ms": {kk: sum(v) / len(v) for kk, v in stage_ms.items()},
+            "ms_per_step_per_rank": per_rank_ms,
             "roofline": {"bound": "hbm", "kernel": "k_emit_small (induced-edge emission + compaction)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

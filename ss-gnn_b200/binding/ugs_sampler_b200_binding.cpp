@@ -1,46 +1,5 @@
-# INTEGRATION — using libugs_b200 from SS-GNN
-
-## 1. Zero-change drop-in (what the repo ships)
-
-The reference trainer picks its sampler by module name (`src/gps/gps/experiment.py:163-178`):
-
-```python
-elif sampler_name == 'ugs':
-    import ugs_sampler
-    self.sampler = ugs_sampler.sample_batch
-```
-
-Put this repo's package directory in front of the reference's compiled extension and nothing else changes:
-
-```bash
-python -c 'import __graft_entry__ as g; g.build()'          # nvcc -gencode arch=compute_100a,code=sm_100a
-export PYTHONPATH=/path/to/repo/ss-gnn_b200:$PYTHONPATH      # ugs_sampler/ (drop-in) + ugs_b200/ (host layer)
-python main.py --config configs/ss_gnn/TUDataset/gcn-mutag.json -o sampler=ugs
-```
-
-`ugs_sampler.sample_batch(edge_index, ptr, m_per_graph, k, mode="sample", seed=42)` keeps the reference signature
-(`src/samplers/ugs_sampler/__init__.pyi:11-56`) and returns the same five tensors
-(`nodes_t[G·m,k]`, `edge_index_t[2,Ē]`, `edge_ptr_t[G·m+1]`, `sample_ptr_t[G+1]`, `edge_src_global_t[Ē]`) as CPU
-pinned int64 tensors, so `_unpack_batch` → `batch.to(device)` (`experiment.py:521-523`) and
-`SubgraphSamplingGNNClassifier.encode_subgraphs` (`models/ss_gnn.py:427-471`) run unmodified.
-Set `UGS_B200_OUTPUT=cuda` (or pass CUDA tensors) to leave the outputs in HBM: `batch.to(device)` is then a no-op
-and the 0.8 KB/graphlet PCIe round trip disappears.
-
-The handle API (`create_preproc / sample / destroy_preproc / has_graphlets / get_preproc_info`,
-`extension.cpp:4-14`) is provided with the same names, defaults and exceptions
-(`RuntimeError("Invalid preproc handle")`, `"mode must be one of: 'sample', 'graph', 'global'"`, …).
-
-## 2. Binding the C ABI directly (what a reference maintainer would add)
-
-`include/ugs_b200.h` is the boundary: `extern "C"`, raw device pointers, sizes, a `cudaStream_t` passed as `void*`,
-`int` status + `ugs_last_error()`. The reference's FFI for this path is pybind11/libtorch
-(`src/samplers/ugs_sampler/src/extension.cpp`); the equivalent binding is either the ctypes stub the repo uses
-(`ss-gnn_b200/ugs_b200/_lib.py`, ~60 lines) or this pybind11 replacement of `sample_batch`
-(`ugs_sampler_batch_extension.cpp:77-300`) — everything the loop over graphs did becomes six calls. The same code is
-kept compilable in `ss-gnn_b200/binding/ugs_sampler_b200_binding.cpp` (built by `__graft_entry__.build()`) and is
-compared bit for bit with the ctypes drop-in in `tests/test_gpu_binding.py`:
-
-```cpp
+// The pybind11/libtorch binding of the C ABI shown in INTEGRATION.md section 2, kept compilable:
+// tests/test_gpu_binding.py builds it against libugs_b200.so and compares it with the ctypes drop-in.
 // ugs_sampler_b200_binding.cpp  -- link with -lugs_b200
 #include <torch/extension.h>
 #include <c10/cuda/CUDAStream.h>
@@ -117,19 +76,9 @@ py::tuple sample_batch(const torch::Tensor& edge_index, const torch::Tensor& ptr
                        int m, int k, const std::string& mode, int seed) {
     return sample_batch_impl(edge_index, ptr, m, k, mode, seed, /*fast=*/1);
 }
-```
 
-| reference interface (file:line) | replaced by |
-|---|---|
-| `slice_and_renumber_edge_index_with_map` `ugs_sampler_batch_extension.cpp:41-75` | `ugs_segment_batch` |
-| `create_preproc` `preproc.cpp:262-284` (`build_csr :32-86`, `compute_1dd_ordering :97-166`, `compute_suffix_and_buckets :176-256`) | `ugs_preproc_batch` |
-| `sample` `sampler.cpp:91-181` (`rand_grow :36-85`, `AliasTable::sample sampler.hpp:72-77`) | `ugs_sample_batch` |
-| edge extraction `sampler.cpp:205-280`, driver post-processing `ugs_sampler_batch_extension.cpp:188-231,257-290` | `ugs_emit_edges` (+ `ugs_count_edges` for caller-provided node rows) |
-| `get_preproc_info` `preproc.cpp:301-314` | `ugs_ginfo` records inside the workspace (`ugs_layout.ginfo`) |
-
-## 3. DDP / multi-GPU
-
-One process per GPU; every rank calls `sample_batch` on its own DataLoader shard. To make the samples independent of
-the number of ranks pass the shard's first **global** graph index as `graph_index_base`
-(`ugs_b200.engine.DeviceBatch.sample(..., graph_index_base=…)`, `ugs_b200/sharding.py`). Nothing on the sampling
-path communicates; `ugs_b200.sharding.gather_stats` all-gathers the six counters (48 B per rank) for logging.
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("sample_batch", &sample_batch, py::arg("edge_index"), py::arg("ptr"), py::arg("m_per_graph"), py::arg("k"),
+          py::arg("mode") = "sample", py::arg("seed") = 42,
+          "Sample m_per_graph k-subgraphs per graph from a batched PyG edge_index + ptr (B200 C-ABI binding).");
+}
