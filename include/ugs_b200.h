@@ -48,6 +48,10 @@ extern "C" {
 #define UGS_MODE_SAMPLE 0
 #define UGS_MODE_GRAPH 1
 #define UGS_MODE_GLOBAL 2
+/* not a reference mode: entries (s*k + j, s*k + l) with s = the batch-wide sample row. This is what the consumer of the
+ * sampler builds from mode "sample" output: edge_index_t + repeat_interleave(arange(B), counts) * k
+ * (gps/models/ss_gnn.py:461-462, ss_gnn_wl.py:283-287), produced here by the emission pass itself. */
+#define UGS_MODE_ENCODER 3
 
 /* sampler variants */
 #define UGS_VARIANT_REF 0      /* the reference law: root ~ b/Z, one rand_grow, no rejection (sampler.cpp:158-181) */
@@ -209,6 +213,22 @@ int ugs_apx_write(int n, int64_t n_columns, int64_t m, int k, uint64_t seed, dou
                   int n_ok, void* workspace, int64_t* samples_out, void* stream);
 int ugs_apx_dump(int n, int64_t nnz, int64_t n_columns, int64_t m, void* workspace, int32_t* rowptr, int32_t* adj,
                  int32_t* order, int32_t* position, double* est, void* stream);
+
+/* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
+ * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in
+ * ss_gnn_wl.py:249-306): global_x = x[nodes.clamp(0)] * (nodes >= 0), global_edge_attr = edge_attr[edge_src],
+ * global_edge_index = edge_index_t + repeat_interleave(arange(B), counts) * k, batch = repeat_interleave(arange(B), k).
+ *
+ * ugs_gather_rows     out[i, :] = index[i] >= 0 ? src[index[i], :] : 0   for rows of row_bytes bytes (any dtype; the
+ *                     copy is bit-exact). Rows with index >= n_src_rows are zero-filled and counted in *n_bad (device
+ *                     int64, may be NULL; the reference raises IndexError for them).
+ * ugs_encoder_offsets for already materialised mode-"sample" output: global_edge_index[2,total] (row 1 at +total) and
+ *                     batch_out[B*k] = i / k. edge_index_s may be NULL (only batch_out is written) and batch_out may
+ *                     be NULL. With ugs_emit_edges(mode = UGS_MODE_ENCODER) the first output needs no extra pass. */
+int ugs_gather_rows(const void* src, int64_t n_src_rows, int64_t row_bytes, const int64_t* index, int64_t n_index,
+                    void* out, int64_t* n_bad, void* stream);
+int ugs_encoder_offsets(const int64_t* edge_index_s, const int64_t* edge_ptr, int64_t B, int k, int64_t total,
+                        int64_t* global_edge_index_out, int64_t* batch_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -609,6 +609,9 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                     else if (mode == UGS_MODE_GRAPH) {
                         const i64 ik = ((i64)t * 32 + sl) * k;
                         av = ik + j; bv = ik + l;
+                    } else if (mode == UGS_MODE_ENCODER) {
+                        const i64 ik = (s0 + sl) * k;
+                        av = ik + j; bv = ik + l;
                     } else {
                         av = lo + s.tile[sl][j]; bv = lo + s.tile[sl][l];
                     }
@@ -678,6 +681,7 @@ k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mod
                         i64 a, b;
                         if (mode == UGS_MODE_SAMPLE) { a = j; b = l; }
                         else if (mode == UGS_MODE_GRAPH) { a = i * k + j; b = i * k + l; }
+                        else if (mode == UGS_MODE_ENCODER) { a = sidx * k + j; b = sidx * k + l; }
                         else { a = lo + u; b = lo + y; }
                         if (o < total) { out_u[o] = a; out_v[o] = b; out_src[o] = (i64)ccol[p]; }
                     }
@@ -825,7 +829,7 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
                               const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
                               void* stream_) {
     if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
-    if (mode < 0 || mode > 2) return ugs_set_error(UGS_EINVAL, "mode must be one of: 'sample', 'graph', 'global'");
+    if (mode < 0 || mode > UGS_MODE_ENCODER) return ugs_set_error(UGS_EINVAL, "mode must be one of: 'sample', 'graph', 'global'");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
     if (G <= 0 || m <= 0 || total <= 0) return UGS_OK;
     if (!nodes || !edge_index_out || !edge_src_out) return ugs_set_error(UGS_EINVAL, "NULL output");

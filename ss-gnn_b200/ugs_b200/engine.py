@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-MODES = {"sample": 0, "graph": 1, "global": 2}
+MODES = {"sample": 0, "graph": 1, "global": 2, "encoder": 3}  # "encoder": UGS_MODE_ENCODER (not a reference mode)
 VARIANTS = {"ref": 0, "uniform": 1}
 CTR = dict(unsorted=0, n_general=1, max_n_general=2, n_skipped=3, total_edges=4, incomplete=5, relaxed=6, trials=7,
            n_large=9)
