@@ -228,13 +228,20 @@ def main():
 
     k, m = KM[args.workload]
     G = args.graphs or DEFAULT_G[args.workload]
-    ei_np, ptr_np = make_workload(args.workload, G, 1234 + rank)
+    # power-law config: ONE huge graph replicated on every rank, its m samples split across ranks;
+    # every other workload: each rank owns its own shard of graphs (weak scaling).
+    sample_sharded = args.workload == "powerlaw" and world > 1
+    ei_np, ptr_np = make_workload(args.workload, G, 1234 + (0 if sample_sharded else rank))
+    ibase, m_job = 0, m
+    if sample_sharded:
+        from ugs_b200 import sharding
+        ibase, m = sharding.shard_samples(m_job, rank, world)
     G = len(ptr_np) - 1
     E = ei_np.shape[1]
     NT = int(ptr_np[-1] - ptr_np[0])
     d_ei = torch.from_numpy(ei_np).to(dev)
     d_ptr = torch.from_numpy(ptr_np).to(dev)
-    gbase = rank * G  # Philox is keyed on the global graph index: results do not depend on the sharding
+    gbase = 0 if sample_sharded else rank * G  # Philox is keyed on the global graph index: results do not depend on the sharding
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -253,7 +260,8 @@ def main():
         e0.record()
         b = DeviceBatch(d_ei, d_ptr, k, int(ptr_np[0]), NT)
         e1.record()
-        outs, stats = b.sample(m, k, "sample", seed=seed, graph_index_base=gbase, emit=False)
+        outs, stats = b.sample(m, k, "sample", seed=seed, graph_index_base=gbase, emit=False,
+                               sample_index_base=ibase)
         e2.record()
         nodes, eidx, eptr, sptr, esrc = outs
         total = stats["n_edge_entries"]
@@ -365,14 +373,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "scaling": "strong" if sample_sharded else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}-shaped batch (BASELINE configs[3]: 1M graphs k=8 m=64 sharded by graph "
                             f"over 8 GPUs -> {G} graphs per rank)" if args.workload == "zinc"
                             else f"{args.workload}-shaped batch",
                 "k": k, "m": m, "graphs_per_rank": G, "nodes_per_rank": NT, "edge_columns_per_rank": E,
                 "mean_edge_entries_per_graphlet": ebar, "l2": "512 MiB flush between timed iterations",
-                "sharding": f"dp{world} by graph, no data-path collective",
+                "sharding": (f"dp{world} by sample of one replicated graph (m={m_job} split), no data-path collective"
+                             if sample_sharded else f"dp{world} by graph, no data-path collective"),
             },
             "stage_ms": {kk: sum(v) / len(v) for kk, v in stage_ms.items()},
             "ms_per_step_per_rank": per_rank_ms,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define UGS_B200_ABI_VERSION 1
+#define UGS_B200_ABI_VERSION 2
 
 /* error codes */
 #define UGS_OK 0
@@ -150,9 +150,13 @@ size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);
 
 /* A.5-A.6 + counts. Writes nodes[G*m,k] (batch-global ids, -1 pad; lo is added for every mode exactly as the
  * batch driver does, :188-196), edge_ptr[G*m+1] (exclusive running totals), sample_ptr[G+1] (= g*m, :130),
- * counters[UGS_CTR_TOTAL_EDGES..]. Randomness: Philox4x32-10 keyed (seed; graph_index_base+g, sample i). */
+ * counters[UGS_CTR_TOTAL_EDGES..]. Randomness: Philox4x32-10 keyed (seed; graph_index_base+g, sample_index_base+i):
+ * a rank that holds graphs [g0,g1) of a batch passes graph_index_base = g0; a rank that draws samples [i0,i1) of
+ * every graph (one huge graph replicated on all ranks) passes m = i1-i0 and sample_index_base = i0.
+ * Either way the rows are the ones a single call over the whole job produces. */
 int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
-                     uint64_t graph_index_base, int variant, int64_t n_general, int64_t max_n_general,
+                     uint64_t graph_index_base, uint64_t sample_index_base, int variant, int64_t n_general,
+                     int64_t max_n_general,
                      void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
                      int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream);
 

@@ -340,6 +340,9 @@ static int grow(const OPreproc* P, int k, i64 root_vi, u64 seed, u64 graph_index
 }
 
 /* sample -- sampler.cpp:91-181 (node rows only). nodes_out: m*k local vertex ids, -1 padded. */
+static u32 g_sample_index_base = 0; /* Philox counter word 0 = g_sample_index_base + i (sample sharding) */
+void oracle_set_sample_index_base(u64 b) { g_sample_index_base = (u32)b; }
+
 int oracle_sample_nodes(const OPreproc* P, int m, int k, u64 seed, u64 graph_index, i32* nodes_out) {
     if (P->n <= 0) return -1; /* "No viable roots available" sampler.cpp:148-150 */
     i64 maxrow = 0;
@@ -348,9 +351,10 @@ int oracle_sample_nodes(const OPreproc* P, int m, int k, u64 seed, u64 graph_ind
     i32* verts = (i32*)malloc(sizeof(i32) * (size_t)(k > 0 ? k : 1));
     for (int i = 0; i < m; ++i) {
         u32 w[4];
-        philox4x32_10((u32)i, 0u, (u32)graph_index, (u32)(graph_index >> 32), (u32)seed, (u32)(seed >> 32), w);
+        const u32 ictr = (u32)i + g_sample_index_base;
+        philox4x32_10(ictr, 0u, (u32)graph_index, (u32)(graph_index >> 32), (u32)seed, (u32)(seed >> 32), w);
         i64 root_vi = draw_root(P, w);
-        int size = grow(P, k, root_vi, seed, graph_index, (u32)i, w, verts, scratch);
+        int size = grow(P, k, root_vi, seed, graph_index, ictr, w, verts, scratch);
         for (int j = 0; j < k; ++j) nodes_out[(i64)i * k + j] = j < size ? verts[j] : -1;
     }
     free(scratch); free(verts);

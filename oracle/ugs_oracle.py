@@ -132,7 +132,7 @@ class Preproc:
 
 
 def sample_batch(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample", seed: int = 42,
-                 graph_index_base: int = 0, given_nodes=None):
+                 graph_index_base: int = 0, given_nodes=None, sample_index_base: int = 0):
     """Oracle counterpart of ugs_sampler.sample_batch (ugs_sampler_batch_extension.cpp:77-300).
 
     Returns numpy (nodes[G*m,k], edge_index[2,E], edge_ptr[G*m+1], sample_ptr[G+1], edge_src[E])."""
@@ -145,6 +145,8 @@ def sample_batch(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample"
     if given_nodes is not None:
         gn = np.ascontiguousarray(np.asarray(given_nodes, dtype=np.int64))
     L = lib()
+    L.oracle_set_sample_index_base.argtypes = [ctypes.c_uint64]
+    L.oracle_set_sample_index_base(int(sample_index_base))  # rows [base, base+m) of the single-call job
     h = L.oracle_sample_batch(_p(r0), _p(r1), r0.shape[0], _p(ptr), G, int(m_per_graph), int(k), MODES[mode],
                               seed & (2**64 - 1), graph_index_base, _p(gn) if gn is not None else None)
     try:
@@ -157,6 +159,7 @@ def sample_batch(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample"
         L.oracle_batch_copy(h, _p(nodes), _p(ei), _p(eptr), _p(sptr), _p(esrc))
     finally:
         L.oracle_batch_free(h)
+        L.oracle_set_sample_index_base(0)
     return nodes, ei, eptr, sptr, esrc
 
 

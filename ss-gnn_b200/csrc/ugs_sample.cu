@@ -93,7 +93,7 @@ __device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& 
 
 template <int KT>
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
-k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
+k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
                int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
                i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
     __shared__ SmallSamp sm_all[SAMP_WARPS];
@@ -155,8 +155,8 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
         i64 cnt = 0;
         if (active) {
-            if (n <= 32) sample_one<u32, KT>(s, gi, n, k, (u32)i, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
-            else sample_one<u64, KT>(s, gi, n, k, (u32)i, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            if (n <= 32) sample_one<u32, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            else sample_one<u64, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
         }
         // ---- coalesced output through the shared tile ------------------------------------------------
         *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
@@ -198,7 +198,7 @@ __device__ __forceinline__ bool in_members(int x, int mine, int size) {
 }
 
 __global__ void __launch_bounds__(256)
-k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase,
+k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
                  i64 n_general, int bm_words, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr) {
     extern __shared__ u32 bm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -228,7 +228,8 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
         const u32 c2 = (u32)gidx, c3 = (u32)(gidx >> 32);
         if (i == 0 && gi.level > 0) n_relaxed++;
 
-        Philox4 r = philox4x32_10((u32)i, 0u, c2, c3, k0, k1);
+        const u32 ictr = (u32)i + ibase;  // Philox counter word 0: the sample's index in the WHOLE job
+        Philox4 r = philox4x32_10(ictr, 0u, c2, c3, k0, k1);
         const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
         int a = 0, b = n - 1;
         while (a < b) {
@@ -247,7 +248,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
             if (step > 0) {
                 if (cutn == 0) break;
                 const int wsel = (step + 1) & 3;
-                if (wsel == 0) r = philox4x32_10((u32)i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
+                if (wsel == 0) r = philox4x32_10(ictr, (u32)((step + 1) >> 2), c2, c3, k0, k1);
                 const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
                 int rsel = (int)__umulhi(wv, (u32)cutn);
                 // r-th set bit of the cut bitmap (ascending vertex id)
@@ -737,14 +738,19 @@ static inline void small_items(int64_t m, int* tiles_per_item, int64_t* items_pe
 }
 
 extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
-                                uint64_t graph_index_base, int variant, int64_t n_general, int64_t max_n_general,
-                                void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
-                                int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream_) {
+                                uint64_t graph_index_base, uint64_t sample_index_base, int variant, int64_t n_general,
+                                int64_t max_n_general, void* workspace, const ugs_layout* L, void* scratch,
+                                size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
+                                void* stream_) {
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
     if (m < 0) return ugs_set_error(UGS_EINVAL, "m_per_graph must be >= 0");
     if (variant != UGS_VARIANT_REF && variant != UGS_VARIANT_UNIFORM) return ugs_set_error(UGS_EINVAL, "unknown variant %d", variant);
-    if (m >= (1ll << 32)) return ugs_set_error(UGS_ELIMIT, "m_per_graph must be < 2^32");
+    if (m >= (1ll << 32) || sample_index_base + (uint64_t)m > (1ull << 32))
+        return ugs_set_error(UGS_ELIMIT, "sample_index_base + m_per_graph must be <= 2^32");
+    if (sample_index_base && variant != UGS_VARIANT_REF)
+        return ugs_set_error(UGS_EINVAL, "sample_index_base is only supported by UGS_VARIANT_REF");
+    const u32 ibase = (u32)sample_index_base;
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
     UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64) * 4, st));
@@ -768,7 +774,7 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
 #define UGS_LAUNCH_SAMPLE(KT_)                                                                                   \
-    k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, tpi, \
+    k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, ibase, tpi, \
                                                             ipg, w, nodes, edge_ptr, sample_ptr)
         switch (k) {
             case 3: UGS_LAUNCH_SAMPLE(3); break;
@@ -795,7 +801,7 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         int64_t blocks = (total + wpb - 1) / wpb;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
-        k_sample_general<<<(unsigned)blocks, wpb * 32, smem, st>>>(ptr, node_base, m, k, seed, graph_index_base,
+        k_sample_general<<<(unsigned)blocks, wpb * 32, smem, st>>>(ptr, node_base, m, k, seed, graph_index_base, ibase,
                                                                   n_general, bm_words, w, nodes, edge_ptr);
         UGS_LAUNCH_CHECK("k_sample_general");
     }

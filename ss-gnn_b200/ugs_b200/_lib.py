@@ -72,7 +72,7 @@ def lib():
     L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, vp, LP, vp]
     L.ugs_sample_scratch_bytes.restype = sz
     L.ugs_sample_scratch_bytes.argtypes = [i64, i64]
-    L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
+    L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
     cd = ctypes.c_double

@@ -46,6 +46,18 @@ def shard(ptr, edge_index, rank: int, world: int, m: int = 1, k: int = 1):
     return np.ascontiguousarray(ei), np.ascontiguousarray(np.asarray(ptr)[g0:g1 + 1]), g0, c0
 
 
+def shard_samples(m: int, rank: int, world: int):
+    """(sample_index_base, m_local) of `rank` when ONE graph (or a small batch of huge graphs) is replicated on every
+    rank and the m samples per graph are split instead of the graphs (section 8e, power-law configs). Passing them to
+    DeviceBatch.sample(m_local, ..., sample_index_base=base) yields rows [base, base+m_local) of the single-rank call."""
+    m, rank, world = int(m), int(rank), int(world)
+    if not (0 <= rank < world):
+        raise ValueError("rank must be in [0, world)")
+    q, r = divmod(max(m, 0), world)
+    base = rank * q + min(rank, r)
+    return base, q + (1 if rank < r else 0)
+
+
 def gather_stats(stats: dict, group=None, device=None) -> dict:
     """All-gather the per-rank statistics vector (the design's only collective) and return summed totals plus
     the per-rank rows. Works with any torch.distributed backend (nccl on GPUs, gloo in the CPU tests)."""

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ugs_b200.h but not exported"
     assert set(_lib.EXPORTS) <= set(names)
-    assert L.ugs_abi_version() == 1
+    assert L.ugs_abi_version() == 2
 
 
 def test_workspace_layout_is_host_only_and_consistent():

@@ -155,6 +155,26 @@ def test_graph_index_base_shards_like_the_whole(cuda_lib):
     assert np.array_equal(shard[4].cpu().numpy() + int(np.nonzero(mask)[0][0]), whole[4].cpu().numpy()[e0:])
 
 
+def test_sample_index_base_shards_like_the_whole(cuda_lib):
+    """Philox counter word 0 is the sample's index in the whole job: drawing samples [i0, i0+m') with
+    sample_index_base=i0 gives rows [i0, i0+m') of every graph of the single call (one huge graph
+    replicated on all ranks, samples split). Both paths (bitmask and general) and the oracle."""
+    rng = np.random.default_rng(21)
+    ei, ptr = random_batch(rng, 9, 5, 40, deg=2.5, weird=False, big=[(2, 130)])
+    k, m, i0, m1 = 4, 50, 17, 20
+    b = _batch(ei, ptr, k)
+    whole, _ = b.sample(m, k, "sample", seed=3)
+    part, _ = b.sample(m1, k, "sample", seed=3, sample_index_base=i0)
+    G = len(ptr) - 1
+    wn = whole[0].cpu().numpy().reshape(G, m, k)
+    assert np.array_equal(part[0].cpu().numpy().reshape(G, m1, k), wn[:, i0:i0 + m1])
+    ref = _oracle_batch(ei, ptr, m1, k, "sample", 3, sample_index_base=i0)
+    for a, r in zip(part, ref):
+        assert np.array_equal(a.cpu().numpy(), r)
+    with pytest.raises(RuntimeError, match="2\\^32"):
+        b.sample(8, k, "sample", seed=3, sample_index_base=2 ** 32 - 4)
+
+
 def test_empty_and_degenerate_inputs(cuda_lib):
     # no graphs
     b = _batch(np.zeros((2, 0), np.int64), np.array([0], np.int64), 3)
