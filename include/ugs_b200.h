@@ -218,6 +218,43 @@ int ugs_apx_write(int n, int64_t n_columns, int64_t m, int k, uint64_t seed, dou
 int ugs_apx_dump(int n, int64_t nnz, int64_t n_columns, int64_t m, void* workspace, int32_t* rowptr, int32_t* adj,
                  int32_t* order, int32_t* position, double* est, void* stream);
 
+/* ---- Random-Walk-with-Restart sampler (reference src/samplers/rwr_sampler/src/rwr_sampler.cpp:72-295) ------------
+ * Same workspace as the UGS path (ugs_segment_batch + ugs_preproc_batch; only the multigraph CSR is used, which is the
+ * reference's adjacency with duplicates, :31-69). ugs_rwr_sample_batch: per sample a uniform seed vertex, then at most
+ * n*k*10 walk steps (restart to the seed with probability p_restart or from a vertex without neighbours, else a uniform
+ * row entry), the first k distinct vertices in visiting order; all -1 rows when the cap is hit or n < k (:139-204).
+ * Writes nodes, scanned per-sample entry counts (edge_ptr), sample_ptr = g*m; counters[UGS_CTR_TRIALS] = walk steps,
+ * counters[UGS_CTR_INCOMPLETE] = failed rows. ugs_rwr_emit_edges: the UGS extraction (rows of the sample in visiting
+ * order, entries in row order) with edge_src = -1 (:217-256); mode "sample" = positions in the row, any other mode =
+ * batch-global node ids. */
+int ugs_rwr_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                         uint64_t graph_index_base, double p_restart, void* workspace, const ugs_layout* L,
+                         void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
+                         void* stream);
+int ugs_rwr_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode, int use_perm,
+                       int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                       const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                       void* stream);
+
+/* ---- exactly uniform sampler by enumeration (reference src/samplers/uniform_sampler/src/uniform_sampler.cpp:86-282) ---
+ * Same workspace as the UGS path (adjacency bitmasks + CSR). Bitmask-path graphs only (n_general must be 0) and
+ * k <= 16: the reference itself tests all C(n,k) combinations per graph (:47-81).
+ *   ugs_enum_count         every connected k-subset counted once (ESU recursion); per-root and per-graph counts go to
+ *                          enum_scratch, their total to counters[UGS_CTR_TOTAL_EDGES] (read it with ugs_batch_info)
+ *   ugs_enum_fill          list[total] = the subsets as 64-bit vertex masks, graph by graph
+ *   ugs_enum_sample_batch  row = ascending vertices of list[graph][mulhi64(Philox word64, count)] (:196-210); all -1
+ *                          rows for graphs without a connected k-subset (:183-191); edge_ptr = scanned per-sample column
+ *                          counts; sample_ptr = g*m. Edges: ugs_eps_emit_edges (same column-scan semantics, :216-245). */
+size_t ugs_enum_scratch_bytes(int64_t G, int64_t NT);
+int ugs_enum_count(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int k, int64_t n_general,
+                   void* workspace, const ugs_layout* L, void* enum_scratch, size_t enum_scratch_bytes, void* stream);
+int ugs_enum_fill(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int k, void* workspace,
+                  const ugs_layout* L, void* enum_scratch, uint64_t* list, int64_t total, void* stream);
+int ugs_enum_sample_batch(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int64_t m, int k, uint64_t seed,
+                          uint64_t graph_index_base, void* workspace, const ugs_layout* L, void* enum_scratch,
+                          const uint64_t* list, void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
+                          int64_t* sample_ptr, void* stream);
+
 /* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
  * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in
  * ss_gnn_wl.py:249-306): global_x = x[nodes.clamp(0)] * (nodes >= 0), global_edge_attr = edge_attr[edge_src],

@@ -8,6 +8,8 @@ The reference C++ (pybind11 + libtorch, no CUDA) is compiled from the sources WH
                                                  it can run on a host without an NVIDIA driver
   oracle/_ref/{pinned,nopin}/epsilon_uniform_sampler.so
   oracle/_ref/{pinned,nopin}/apx_ugs_sampler.so
+  oracle/_ref/{pinned,nopin}/uniform_sampler.so
+  oracle/_ref/{pinned,nopin}/rwr_sampler.so
 
 `oracle/_ref/` is git-ignored but NOT gpurun-ignored: the built files travel to the GPU box, where
 /root/reference does not exist. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
@@ -86,6 +88,10 @@ def build_all(variants=("pinned", "nopin")):
         built[(v, "uniform_sampler")] = _compile(
             "uniform_sampler", [os.path.join(uni, "src", "uniform_sampler.cpp")],
             os.path.join(uni, "include"), v, ["-fopenmp"], ["-fopenmp"])
+        rwr = os.path.join(S, "rwr_sampler")
+        built[(v, "rwr_sampler")] = _compile(
+            "rwr_sampler", [os.path.join(rwr, "src", "rwr_sampler.cpp")],
+            os.path.join(rwr, "src"), v, ["-fopenmp"], ["-fopenmp"])
     return built
 
 

@@ -121,3 +121,56 @@ def p_epsilon(rows, k: int, eps: float, max_attempts=None):
             out[key] = v * scale
     out[()] = (1.0 - A) ** max_attempts if A < 1 else 0.0
     return out
+
+
+def p_rwr(rows, k: int, p_restart: float, steps: int = 4000):
+    """Law of one output row of rwr_sampler (rwr_sampler.cpp:165-204) as {tuple(visiting order): prob, (): failure},
+    ignoring the n*k*10 step cap (its truncated mass is far below the test resolution on the small cases it is used
+    for, except where the walk cannot reach k vertices at all -- that mass lands in () here as well).
+    rows = adjacency lists WITH duplicates. The walk inside the current set S is a Markov chain with restart; the
+    distribution of the first vertex outside S it steps on is accumulated over `steps` transitions."""
+    n = len(rows)
+    out = defaultdict(float)
+    if n < k or n == 0:
+        return {(): 1.0}
+
+    def exits(seq, cur):
+        """{new vertex: prob} for the walk at `cur` with visited sequence seq (seq[0] = seed)."""
+        S = set(seq)
+        seed = seq[0]
+        dist = {cur: 1.0}
+        ex = defaultdict(float)
+        for _ in range(steps):
+            nd = defaultdict(float)
+            for u, pu in dist.items():
+                if pu < 1e-18:
+                    continue
+                if not rows[u]:
+                    nd[seed] += pu
+                    continue
+                nd[seed] += pu * p_restart
+                share = pu * (1.0 - p_restart) / len(rows[u])
+                if share == 0.0:
+                    continue
+                for v in rows[u]:
+                    if v in S:
+                        nd[v] += share
+                    else:
+                        ex[v] += share
+            dist = nd
+            if sum(dist.values()) < 1e-15:
+                break
+        return ex, sum(dist.values())
+
+    def rec(seq, cur, p):
+        if len(seq) == k:
+            out[tuple(seq)] += p
+            return
+        ex, stuck = exits(seq, cur)
+        out[()] += p * stuck
+        for v, pv in ex.items():
+            rec(seq + [v], v, p * pv)
+
+    for s in range(n):
+        rec([s], s, 1.0 / n)
+    return {key: v for key, v in out.items() if v > 0}

@@ -18,7 +18,7 @@ MODES = {"sample": 0, "graph": 1, "global": 2}
 
 def build(force: bool = False) -> str:
     out = os.path.join(HERE, "libugs_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ugs_oracle.c", "eps_oracle.c", "uni_oracle.c", "apx_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("ugs_oracle.c", "eps_oracle.c", "uni_oracle.c", "apx_oracle.c", "walk_oracle.c")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-std=c11", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"])

@@ -69,6 +69,7 @@ class DeviceBatch:
         (every PyG batch); the kernels verify it and `_late_check` redoes the batch on the slow path otherwise."""
         L = _lib.lib()
         self.perm = None
+        self._enum = None
         self._fast = fast
         with torch.cuda.device(self.device):
             self._segment(fast)
@@ -234,6 +235,108 @@ class DeviceBatch:
             total = int(edge_ptr[-1].item()) if given_nodes is not None else info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_trials=info[CTR["trials"]], n_skipped_graphs=self.n_skipped,
+                         n_general_graphs=self.n_general)
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_eps_emit_edges(_ptr(self.edge_index), self.E, _ptr(self.ptr), G, self.node_base, m, k, md,
+                                            _ptr(self.perm), self.n_general, _ptr(self.ws), ctypes.byref(self.layout),
+                                            _ptr(nodes), _ptr(edge_ptr), total, _ptr(edge_index), _ptr(edge_src),
+                                            _stream()))
+        return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
+
+    def sample_rwr(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42, p_restart: float = 0.2,
+                   graph_index_base: int = 0):
+        """rwr_sampler.sample_batch on the device (rwr_sampler.cpp:72-295): same 5-tuple layout, node rows in
+        visiting order, UGS-style entries (both directions, duplicates kept), edge_src = -1."""
+        L = _lib.lib()
+        k = self.k if k is None else int(k)
+        if k < 1:
+            raise RuntimeError("k must be >= 1")
+        if not (p_restart >= 0.0 and p_restart <= 1.0):
+            raise RuntimeError("p_restart in [0,1]")
+        m = int(m)
+        G = max(self.G, 0)
+        dev = self.device
+        md = MODES["sample"] if mode == "sample" else MODES["global"]
+        with torch.cuda.device(dev):
+            nodes = torch.empty((G * m, k), dtype=torch.int64, device=dev)
+            edge_ptr = torch.empty(G * m + 1, dtype=torch.int64, device=dev)
+            sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+            sbytes = int(L.ugs_sample_scratch_bytes(G, m))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.ugs_rwr_sample_batch(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
+                                              graph_index_base, float(p_restart), _ptr(self.ws),
+                                              ctypes.byref(self.layout), _ptr(scratch), sbytes, _ptr(nodes),
+                                              _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
+            info = self.info()
+            if self._late_check(info):
+                return self.sample_rwr(m, k, mode, seed, p_restart, graph_index_base)
+            total = info[CTR["total_edges"]]
+            stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
+                         n_walk_steps=info[CTR["trials"]], n_skipped_graphs=self.n_skipped,
+                         n_general_graphs=self.n_general)
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_rwr_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, md,
+                                            1 if self.perm is not None else 0, self.n_general, _ptr(self.ws),
+                                            ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr), total,
+                                            _ptr(edge_index), _ptr(edge_src), _stream()))
+        return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
+
+    def enumerate_connected(self, k: int | None = None):
+        """All connected k-subsets of every graph (uniform_sampler.cpp:47-81) as 64-bit vertex masks:
+        (list[T] int64 bit patterns, graph_off[G+1]). Cached per k; bitmask-path graphs only."""
+        L = _lib.lib()
+        k = self.k if k is None else int(k)
+        if k != self.k:
+            raise RuntimeError(f"this batch was preprocessed for k={self.k}")
+        cache = getattr(self, "_enum", None)
+        if cache is not None and cache[0] == k:
+            return cache[1], cache[2]
+        self._ensure_valid()
+        G = max(self.G, 0)
+        dev = self.device
+        with torch.cuda.device(dev):
+            sb = int(L.ugs_enum_scratch_bytes(G, self.NT))
+            es = torch.empty(sb, dtype=torch.uint8, device=dev)
+            _lib.check(L.ugs_enum_count(_ptr(self.ptr), G, self.NT, self.node_base, k, self.n_general, _ptr(self.ws),
+                                        ctypes.byref(self.layout), _ptr(es), sb, _stream()))
+            total = self.info()[CTR["total_edges"]]
+            lst = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_enum_fill(_ptr(self.ptr), G, self.NT, self.node_base, k, _ptr(self.ws),
+                                       ctypes.byref(self.layout), _ptr(es), _ptr(lst), total, _stream()))
+        self._enum = (k, lst, es)
+        return lst, es
+
+    def enum_graph_offsets(self, es: torch.Tensor) -> torch.Tensor:
+        G = max(self.G, 0)
+        return es[8 * self.NT: 8 * (self.NT + G + 1)].view(torch.int64)
+
+    def sample_uniform_enum(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
+                            graph_index_base: int = 0):
+        """uniform_sampler.sample_batch on the device (uniform_sampler.cpp:86-282): one enumerated connected k-subset
+        per sample, uniformly; ascending node rows; one edge entry per batch column inside the sample."""
+        L = _lib.lib()
+        k = self.k if k is None else int(k)
+        m = int(m)
+        G = max(self.G, 0)
+        dev = self.device
+        md = MODES.get(mode, 2) if mode == "sample" else 2
+        lst, es = self.enumerate_connected(k)
+        with torch.cuda.device(dev):
+            nodes = torch.empty((G * m, k), dtype=torch.int64, device=dev)
+            edge_ptr = torch.empty(G * m + 1, dtype=torch.int64, device=dev)
+            sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+            sbytes = int(L.ugs_sample_scratch_bytes(G, m))
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.ugs_enum_sample_batch(_ptr(self.ptr), G, self.NT, self.node_base, m, k, seed & (2 ** 64 - 1),
+                                               graph_index_base, _ptr(self.ws), ctypes.byref(self.layout), _ptr(es),
+                                               _ptr(lst), _ptr(scratch), sbytes, _ptr(nodes), _ptr(edge_ptr),
+                                               _ptr(sample_ptr), _stream()))
+            info = self.info()
+            total = info[CTR["total_edges"]]
+            stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
+                         n_enumerated=int(lst.numel()), n_skipped_graphs=self.n_skipped,
                          n_general_graphs=self.n_general)
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
