@@ -153,10 +153,13 @@ size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);
  * counters[UGS_CTR_TOTAL_EDGES..]. Randomness: Philox4x32-10 keyed (seed; graph_index_base+g, sample_index_base+i):
  * a rank that holds graphs [g0,g1) of a batch passes graph_index_base = g0; a rank that draws samples [i0,i1) of
  * every graph (one huge graph replicated on all ranks) passes m = i1-i0 and sample_index_base = i0.
- * Either way the rows are the ones a single call over the whole job produces. */
+ * Either way the rows are the ones a single call over the whole job produces.
+ * seed_mode 0: as above. seed_mode 1: key = seed + graph_index_base + g and graph counter 0, i.e. graph g gets the rows
+ * a single-graph call with seed + (graph_index_base + g) produces -- the reference's presampling loop
+ * (gps/experiment.py:405-417: one call per dataset graph with seed = cfg.seed + index) as ONE batch call. */
 int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
-                     uint64_t graph_index_base, uint64_t sample_index_base, int variant, int64_t n_general,
-                     int64_t max_n_general,
+                     uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                     int64_t n_general, int64_t max_n_general,
                      void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
                      int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream);
 
@@ -254,6 +257,26 @@ int ugs_enum_sample_batch(const int64_t* ptr, int64_t G, int64_t NT, int64_t nod
                           uint64_t graph_index_base, void* workspace, const ugs_layout* L, void* enum_scratch,
                           const uint64_t* list, void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
                           int64_t* sample_ptr, void* stream);
+
+/* ---- presample store: re-stitching cached samples into a mini-batch ---------------------------
+ * Replaces Experiment._setup_presampling / _load_from_presample_cache (gps/experiment.py:379-440,895-995). The store
+ * (s_*) is the output of one ugs_sample_batch(seed_mode = 1, mode "sample") call over a whole dataset split of Gd
+ * graphs, kept in HBM, plus that batch's ptr (s_ptr) and per-graph first columns (s_cstart = workspace cstart).
+ *   ugs_presample_plan  per-slot entry counts and the mini-batch's per-graph column offsets (:926-932), scanned into
+ *                       scratch; *h_total = entries of the stitched mini-batch (synchronises the stream).
+ *                       graph_idx[Gb] = dataset indices; ptr[Gb+1], edge_index_row0[E] = the mini-batch itself.
+ *   ugs_presample_load  nodes (cached local ids + ptr[b]; keep_padding = 0 adds ptr[b] to the -1 padding too, exactly
+ *                       like :957-958), unchanged local edge_index, edge_src re-based to the mini-batch's columns
+ *                       (:966), edge_ptr / sample_ptr running totals (:973-981). */
+size_t ugs_presample_scratch_bytes(int64_t Gb);
+int ugs_presample_plan(const int64_t* s_edge_ptr, int64_t Gd, int64_t m, const int64_t* graph_idx, int64_t Gb,
+                       const int64_t* ptr, const int64_t* edge_index_row0, int64_t E, void* scratch,
+                       size_t scratch_bytes, int64_t* h_total, void* stream);
+int ugs_presample_load(const int64_t* s_nodes, const int64_t* s_edge_index, int64_t s_total, const int64_t* s_edge_ptr,
+                       const int64_t* s_edge_src, const int64_t* s_ptr, const int64_t* s_cstart, int64_t Gd, int64_t m,
+                       int k, const int64_t* graph_idx, int64_t Gb, const int64_t* ptr, const void* scratch,
+                       int64_t total, int keep_padding, int64_t* nodes_out, int64_t* edge_index_out,
+                       int64_t* edge_ptr_out, int64_t* sample_ptr_out, int64_t* edge_src_out, void* stream);
 
 /* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
  * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in

@@ -53,7 +53,7 @@ static py::tuple sample_batch_impl(const torch::Tensor& edge_index, const torch:
     const size_t sb = ugs_sample_scratch_bytes(G, m);
     auto scratch = torch::empty({(int64_t)sb}, u8);
     chk(ugs_sample_batch(p.data_ptr<int64_t>(), G, base, m, k, (uint64_t)seed, /*graph_index_base=*/0,
-                         /*sample_index_base=*/0, UGS_VARIANT_REF, info[UGS_CTR_N_GENERAL], info[UGS_CTR_MAX_N_GENERAL], ws.data_ptr(), &L,
+                         /*sample_index_base=*/0, /*seed_mode=*/0, UGS_VARIANT_REF, info[UGS_CTR_N_GENERAL], info[UGS_CTR_MAX_N_GENERAL], ws.data_ptr(), &L,
                          scratch.data_ptr(), sb, nodes.data_ptr<int64_t>(), edge_ptr.data_ptr<int64_t>(),
                          sample_ptr.data_ptr<int64_t>(), st));
     chk(ugs_batch_info(ws.data_ptr(), &L, info, st));               // syncs; info[4] = total emitted entries

@@ -94,7 +94,7 @@ __device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& 
 template <int KT>
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
 k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
-               int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
+               int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
                i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
     __shared__ SmallSamp sm_all[SAMP_WARPS];
     if (KT) k = KT;
@@ -146,7 +146,10 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
     __syncwarp();
 
     const u64 gidx = gbase + (u64)g;
-    const u32 c2 = (u32)gidx, c3 = (u32)(gidx >> 32), k0 = (u32)seed, k1 = (u32)(seed >> 32);
+    // seed_mode 1: key = seed + graph index, graph counter 0 -- what a loop of single-graph calls with seed + i draws
+    const u64 kseed = seed_mode ? seed + gidx : seed;
+    const u64 cg = seed_mode ? 0ull : gidx;
+    const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
     int n_incomplete = 0;
 
     for (int t = t0; t < t1; ++t) {
@@ -199,7 +202,7 @@ __device__ __forceinline__ bool in_members(int x, int mine, int size) {
 
 __global__ void __launch_bounds__(256)
 k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
-                 i64 n_general, int bm_words, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr) {
+                 int seed_mode, i64 n_general, int bm_words, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr) {
     extern __shared__ u32 bm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     u32* bm = bm_all + (size_t)warp * bm_words;
@@ -208,7 +211,6 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
     const u32 lt_mask = (1u << lane) - 1u;
     const i64 total = n_general * m;
     const i64 nwarps = (i64)gridDim.x * wpb;
-    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
     unsigned long long n_incomplete = 0, n_relaxed = 0;
 
     for (i64 t = (i64)blockIdx.x * wpb + warp; t < total; t += nwarps) {
@@ -225,7 +227,9 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
         const double* cm = w.cum + nb;
         const i32* cidx = w.csr_idx + 2 * w.cstart[g];
         const u64 gidx = gbase + (u64)g;
-        const u32 c2 = (u32)gidx, c3 = (u32)(gidx >> 32);
+        const u64 kseed = seed_mode ? seed + gidx : seed;
+        const u64 cg = seed_mode ? 0ull : gidx;
+        const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
         if (i == 0 && gi.level > 0) n_relaxed++;
 
         const u32 ictr = (u32)i + ibase;  // Philox counter word 0: the sample's index in the WHOLE job
@@ -738,8 +742,8 @@ static inline void small_items(int64_t m, int* tiles_per_item, int64_t* items_pe
 }
 
 extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
-                                uint64_t graph_index_base, uint64_t sample_index_base, int variant, int64_t n_general,
-                                int64_t max_n_general, void* workspace, const ugs_layout* L, void* scratch,
+                                uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                                int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L, void* scratch,
                                 size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
                                 void* stream_) {
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
@@ -750,6 +754,9 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         return ugs_set_error(UGS_ELIMIT, "sample_index_base + m_per_graph must be <= 2^32");
     if (sample_index_base && variant != UGS_VARIANT_REF)
         return ugs_set_error(UGS_EINVAL, "sample_index_base is only supported by UGS_VARIANT_REF");
+    if (seed_mode != 0 && seed_mode != 1) return ugs_set_error(UGS_EINVAL, "seed_mode must be 0 or 1");
+    if (seed_mode && variant != UGS_VARIANT_REF)
+        return ugs_set_error(UGS_EINVAL, "seed_mode 1 is only supported by UGS_VARIANT_REF");
     const u32 ibase = (u32)sample_index_base;
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
@@ -774,8 +781,8 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
 #define UGS_LAUNCH_SAMPLE(KT_)                                                                                   \
-    k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, ibase, tpi, \
-                                                            ipg, w, nodes, edge_ptr, sample_ptr)
+    k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, ibase, \
+                                                            seed_mode, tpi, ipg, w, nodes, edge_ptr, sample_ptr)
         switch (k) {
             case 3: UGS_LAUNCH_SAMPLE(3); break;
             case 4: UGS_LAUNCH_SAMPLE(4); break;
@@ -802,7 +809,7 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         k_sample_general<<<(unsigned)blocks, wpb * 32, smem, st>>>(ptr, node_base, m, k, seed, graph_index_base, ibase,
-                                                                  n_general, bm_words, w, nodes, edge_ptr);
+                                                                  seed_mode, n_general, bm_words, w, nodes, edge_ptr);
         UGS_LAUNCH_CHECK("k_sample_general");
     }
     return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);

@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -20,6 +20,7 @@ EXPORTS = [
     "ugs_sort_scratch_bytes", "ugs_sort_columns", "ugs_apx_workspace_bytes", "ugs_apx_prepare", "ugs_apx_trials", "ugs_apx_write", "ugs_apx_dump",
     "ugs_gather_rows", "ugs_encoder_offsets", "ugs_rwr_sample_batch", "ugs_rwr_emit_edges",
     "ugs_enum_scratch_bytes", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
+    "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
 ]
 
 
@@ -73,7 +74,7 @@ def lib():
     L.ugs_preproc_batch.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, vp, LP, vp]
     L.ugs_sample_scratch_bytes.restype = sz
     L.ugs_sample_scratch_bytes.argtypes = [i64, i64]
-    L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, u64, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
+    L.ugs_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, u64, ci, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_emit_edges.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_count_edges.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp, vp, vp]
     cd = ctypes.c_double
@@ -98,6 +99,11 @@ def lib():
     L.ugs_enum_count.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp]
     L.ugs_enum_fill.argtypes = [vp, i64, i64, i64, ci, vp, LP, vp, vp, i64, vp]
     L.ugs_enum_sample_batch.argtypes = [vp, i64, i64, i64, i64, ci, u64, u64, vp, LP, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.ugs_presample_scratch_bytes.restype = sz
+    L.ugs_presample_scratch_bytes.argtypes = [i64]
+    L.ugs_presample_plan.argtypes = [vp, i64, i64, vp, i64, vp, vp, i64, vp, sz, ctypes.POINTER(i64), vp]
+    L.ugs_presample_load.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, i64, ci, vp, i64, vp, vp, i64, ci,
+                                     vp, vp, vp, vp, vp, vp]
     _LIB = L
     return L
 

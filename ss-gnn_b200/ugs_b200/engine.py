@@ -159,7 +159,7 @@ class DeviceBatch:
     # ------------------------------------------------------------------------------------------------
     def sample(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
                graph_index_base: int = 0, variant: str | None = None, emit: bool = True,
-               sample_index_base: int = 0):
+               sample_index_base: int = 0, per_graph_seed: bool = False):
         """Returns device tensors (nodes[G*m,k], edge_index[2,Ebar], edge_ptr[G*m+1], sample_ptr[G+1],
         edge_src[Ebar]) and the stats dict. One host sync (reading Ebar) between sampling and emission."""
         L = _lib.lib()
@@ -179,13 +179,15 @@ class DeviceBatch:
             sbytes = int(L.ugs_sample_scratch_bytes(G, m))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
             _lib.check(L.ugs_sample_batch(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
-                                          graph_index_base, int(sample_index_base), VARIANTS[variant], self.n_general,
+                                          graph_index_base, int(sample_index_base), 1 if per_graph_seed else 0,
+                                          VARIANTS[variant], self.n_general,
                                           self.max_n_general,
                                           _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch), sbytes,
                                           _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
             info = self.info()
             if self._late_check(info):
-                return self.sample(m, k, mode, seed, graph_index_base, variant, emit, sample_index_base)
+                return self.sample(m, k, mode, seed, graph_index_base, variant, emit, sample_index_base,
+                                   per_graph_seed)
             total = info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
