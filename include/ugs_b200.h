@@ -278,6 +278,20 @@ int ugs_presample_load(const int64_t* s_nodes, const int64_t* s_edge_index, int6
                        int64_t total, int keep_padding, int64_t* nodes_out, int64_t* edge_index_out,
                        int64_t* edge_ptr_out, int64_t* sample_ptr_out, int64_t* edge_src_out, void* stream);
 
+/* ---- Weisfeiler-Lehman graphlet classification ----------------------------------------------
+ * Replaces compute_wl_hash + extract_subgraph_from_batch (gps/utils/wl_vocab.py:21-108) and the per-sample loop
+ * SubgraphSamplingGNNWithWL._compute_wl_ids (gps/models/ss_gnn_wl.py:210-247) for use_node_features = False.
+ *   ugs_wl_hash    digest_out[B][2] = the 16-byte BLAKE2b digest whose hex string is exactly what
+ *                  nx.weisfeiler_lehman_graph_hash(G, node_attr = str(degree), iterations) returns for the sample's
+ *                  nx.Graph (memory order = hex order); num_nodes_out[B] = #(row entries >= 0), 0 = "unknown id".
+ *                  edge_index_s: the sampler's mode-"sample" output [2,total] (row 1 at +total). k <= 16.
+ *   ugs_wl_lookup  ids_out[s] = vocab_ids[i] where vocab_keys[i] (two big-endian uint64 per hash, sorted ascending =
+ *                  hex-string order) equals digest s; unknown_id when absent or num_nodes == 0 (hash_to_id, :206-217). */
+int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index_s, int64_t total,
+                const int64_t* edge_ptr, int iterations, uint64_t* digest_out, int32_t* num_nodes_out, void* stream);
+int ugs_wl_lookup(const uint64_t* digest, const int32_t* num_nodes, int64_t B, const uint64_t* vocab_keys,
+                  const int64_t* vocab_ids, int64_t V, int64_t unknown_id, int64_t* ids_out, void* stream);
+
 /* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
  * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in
  * ss_gnn_wl.py:249-306): global_x = x[nodes.clamp(0)] * (nodes >= 0), global_edge_attr = edge_attr[edge_src],

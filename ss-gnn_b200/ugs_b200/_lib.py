@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -21,6 +21,7 @@ EXPORTS = [
     "ugs_gather_rows", "ugs_encoder_offsets", "ugs_rwr_sample_batch", "ugs_rwr_emit_edges",
     "ugs_enum_scratch_bytes", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
+    "ugs_wl_hash", "ugs_wl_lookup",
 ]
 
 
@@ -104,6 +105,8 @@ def lib():
     L.ugs_presample_plan.argtypes = [vp, i64, i64, vp, i64, vp, vp, i64, vp, sz, ctypes.POINTER(i64), vp]
     L.ugs_presample_load.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, i64, ci, vp, i64, vp, vp, i64, ci,
                                      vp, vp, vp, vp, vp, vp]
+    L.ugs_wl_hash.argtypes = [vp, i64, ci, vp, i64, vp, ci, vp, vp, vp]
+    L.ugs_wl_lookup.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp]
     _LIB = L
     return L
 
