@@ -61,6 +61,45 @@ def test_dropin_signatures_match_the_reference_stubs():
         us.sample(12345, 1, 3)
 
 
+def test_all_five_sampler_modules_keep_the_reference_signatures():
+    """src/samplers/*/__init__.pyi and the py::arg lists of the five pybind11 modules (rwr_sampler.cpp:297-308,
+    uniform_sampler.cpp:287-295, epsilon_uniform_sampler.cpp:367-377, apx_ugs_sampler.cpp:529-538)."""
+    import apx_ugs_sampler
+    import epsilon_uniform_sampler
+    import rwr_sampler
+    import uniform_sampler
+    base = ["edge_index", "ptr", "m_per_graph", "k", "mode", "seed"]
+    for mod, extra in ((rwr_sampler, [("p_restart", 0.2)]), (uniform_sampler, []),
+                       (epsilon_uniform_sampler, [("epsilon", 0.1)]), (apx_ugs_sampler, [("epsilon", 0.1)])):
+        sig = inspect.signature(mod.sample_batch)
+        public = [n for n in sig.parameters if not n.startswith("_")]  # apx has a private test hook (_max_trials)
+        assert public == base + [n for n, _ in extra], mod.__name__
+        assert sig.parameters["mode"].default == "sample" and sig.parameters["seed"].default == 42
+        for n, d in extra:
+            assert sig.parameters[n].default == d
+
+
+def test_host_side_modules_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from ugs_b200 import encode, presample, wl
+    x = torch.zeros(4, 2)
+    idx = torch.zeros(3, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        encode.gather_rows(x, idx)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        wl.wl_digests(torch.zeros((1, 3), dtype=torch.long), torch.zeros((2, 0), dtype=torch.long),
+                      torch.zeros(2, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        presample.PresampleStore.build(torch.zeros((2, 0), dtype=torch.long), torch.zeros(1, dtype=torch.long), 2, 3)
+    import rwr_sampler
+    import uniform_sampler
+    for mod in (rwr_sampler, uniform_sampler):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.sample_batch(torch.tensor([[0, 1], [1, 2]]), torch.tensor([0, 3]), 2, 2)
+
+
 def test_dropin_argument_errors_and_no_cpu_fallback():
     import torch
     import ugs_sampler as us
