@@ -8,7 +8,7 @@ while IFS='=' read -r name flags; do [ -n "$name" ] && V[$name]="$flags"; done <
 if [ "$1" = build ]; then
   for name in "${!V[@]}"; do
     nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --extended-lambda -Xcompiler -fPIC -shared \
-      -Iinclude -I$CS ${V[$name]} $CS/ugs_preproc.cu $CS/ugs_preproc_large.cu $CS/ugs_sortcols.cu $CS/ugs_sample.cu $CS/ugs_variants.cu $CS/ugs_apx.cu $CS/ugs_capi.cu -o build_variants/lib_$name.so &
+      -Iinclude -I$CS ${V[$name]} $CS/*.cu -o build_variants/lib_$name.so &
   done; wait; ls build_variants
 else
   for name in $(echo "${!V[@]}" | tr ' ' '\n' | sort); do

@@ -104,8 +104,11 @@ struct __align__(16) SmallPre {
     unsigned char index_of[64];
 };
 
+#ifndef PRE_MINB
+#define PRE_MINB 6  // min resident CTAs per SM asked of the compiler: 40 registers, 48 warps/SM (B200 A/B: 5 -> 0.389 ms,
+#endif              // 6 -> 0.373 ms, 7 -> 0.405 ms with spills)
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, PRE_MINB)
 k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, const i64* __restrict__ ptr,
                 i64 G, i64 node_base, int k, const i64* __restrict__ perm, WS w) {
     __shared__ SmallPre sm_all[WARPS];

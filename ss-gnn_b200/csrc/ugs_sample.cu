@@ -11,6 +11,15 @@
 #include "ugs_common.cuh"
 
 #define SAMP_WARPS 8
+// Measured on B200 (profiles/README.md, A/B of the ZINC-shaped step): 4 resident CTAs (64 registers, 32 bytes of
+// spill) 0.444 -> 0.412 ms, plus per-thread 16-byte row stores -> 0.406 ms; 5 CTAs (48 registers) is slower again.
+// (Selecting the r-th cut bit by clearing r low bits instead of the popc search was slower: 0.61 ms.)
+#ifndef SAMP_MINB
+#define SAMP_MINB 4      // min resident CTAs per SM asked of the compiler (register budget)
+#endif
+#ifndef SAMP_VECSTORE
+#define SAMP_VECSTORE 1  // 1: every thread stores its own node row with 16-byte stores (even k <= 8)
+#endif
 
 // =====================================================================================================
 // Bitmask path: sample + count
@@ -92,7 +101,7 @@ __device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& 
 }
 
 template <int KT>
-__global__ void __launch_bounds__(SAMP_WARPS * 32)
+__global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
 k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
                int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
                i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
@@ -161,11 +170,25 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
             if (n <= 32) sample_one<u32, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
             else sample_one<u64, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
         }
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+#if SAMP_VECSTORE
+        if (KT > 0 && KT <= 8 && (KT & 1) == 0) {
+            // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
+            if (active) {
+                longlong2* out = reinterpret_cast<longlong2*>(nodes_out + (s0 + lane) * KT);
+#pragma unroll
+                for (int q = 0; q < KT / 2; ++q) {
+                    const u32 b0 = (u32)(nlo >> (16 * q)) & 0xFFu, b1 = (u32)(nlo >> (16 * q + 8)) & 0xFFu;
+                    out[q] = make_longlong2((b0 == 0xFFu) ? (i64)-1 : lo + (i64)b0, (b1 == 0xFFu) ? (i64)-1 : lo + (i64)b1);
+                }
+            }
+        } else
+#endif
+        {
         // ---- coalesced output through the shared tile ------------------------------------------------
         *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
         __syncwarp();
-        const i64 s0 = g * m + (i64)t * 32;
-        const int nv = (int)min((i64)32, m - (i64)t * 32);
         {
             int sidx = lane / k, j = lane - sidx * k;
             i64* out = nodes_out + s0 * k;
@@ -175,6 +198,7 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
                 j += r32; sidx += q32;
                 if (j >= k) { j -= k; sidx++; }
             }
+        }
         }
         if (active) edge_ptr[1 + s0 + lane] = cnt;
         __syncwarp();
@@ -443,8 +467,13 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 #ifndef EMIT_WARPS
 #define EMIT_WARPS 8
 #endif
+// (Prefetching the tile's node rows / offsets to L2 at kernel entry changed nothing: 1.272 vs 1.274 ms.)
 #define EMIT_STAGE 1280  // staged entries per flush; a sample never has more than 768 (= 2 * max columns)
 #define LMAP_STRIDE 68   // 17 words: the 32 per-sample rows start in 32 different banks
+
+#ifndef EMIT_MINB
+#define EMIT_MINB 5    // resident CTAs per SM the NARROW kernel is compiled for (48 registers)
+#endif
 
 template <typename StageT>
 struct __align__(16) SmallEmit {
@@ -454,30 +483,51 @@ struct __align__(16) SmallEmit {
     unsigned char lmap[32][LMAP_STRIDE];    // local vertex id -> position inside its sample, 0xFF = not a member
     unsigned short ent[2 * UGS_SMALL_MAX_COLS];  // CSR entry: neighbour id | payload << 6
 };
+// B200 A/B of the ZINC-shaped step (profiles/README.md): byte lmap, 4 CTAs/SM 1.27-1.29 ms; nibble lmap, 4 CTAs 1.27 ms;
+// nibble lmap + 5 CTAs (40 warps/SM) 1.22 ms. Membership / local index from registers (vertex mask + packed
+// rank->position map, no lmap at all, 4.6 KB per warp) was slower at equal occupancy: 1.35 ms (4 CTAs), 1.24-1.26 (5).
+#ifndef EMIT_NIBBLE
+#define EMIT_NIBBLE 1  // NARROW path: lmap[] holds 4-bit positions (36-byte rows), staging trimmed so that 5 CTAs fit an SM
+#endif
+#define NIB_STRIDE 36  // 9 words: the 32 per-sample rows start in 32 different banks
+#define NIB_STAGE 1232
+#if EMIT_NIBBLE
+template <>
+struct __align__(16) SmallEmit<unsigned short> {  // 5664 bytes per warp: 5 CTAs of 8 warps per SM
+    unsigned short stage[NIB_STAGE];
+    u32 rowrange[64];
+    unsigned char tile[32][8];
+    unsigned char lmap[32][NIB_STRIDE];  // two vertices per byte: position (0..7) or 0xF = not a member
+    unsigned short ent[2 * UGS_SMALL_MAX_COLS];
+};
+#endif
 // payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
 // when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
 
 // NARROW: k <= 8 and mode "sample": staged entry = payload << 6 | l << 3 | j          (16 bits)
 // else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
 template <bool NARROW>
-__global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? 4 : 3)
+__global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
              i64* __restrict__ out_src) {
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
+    constexpr bool NIBBLE = NARROW && (EMIT_NIBBLE != 0);  // k <= 8: two vertices per lmap byte
+    constexpr int STAGE_N = (int)(sizeof(SmallEmit<stage_t>::stage) / sizeof(stage_t));
+    constexpr int LROW_BYTES = (int)sizeof(SmallEmit<stage_t>::lmap) / 32;
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
     const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
     if (g >= G) return;
-    const ugs_ginfo gi = w.ginfo[g];
-    if (gi.cls != 1 || gi.nnz == 0) return;
     const int chunk = (int)(item - g * items_per_graph);
     const int ntiles = (int)((m + 31) >> 5);
     const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
     if (t0 >= t1) return;
+    const ugs_ginfo gi = w.ginfo[g];
+    if (gi.cls != 1 || gi.nnz == 0) return;
     const i64 lo = ptr[g];
     const int n = (int)(ptr[g + 1] - lo);
     const i64 nb = lo - node_base;
@@ -498,7 +548,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         }
         u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
 #pragma unroll
-        for (int q = 0; q < LMAP_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
+        for (int q = 0; q < LROW_BYTES / 4; ++q) row[q] = 0xFFFFFFFFu;
     }
     unsigned char* lrow = &s.lmap[lane][0];
     const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent);
@@ -530,16 +580,28 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         u32 nb4[4] = {~0u, ~0u, ~0u, ~0u};
         const bool walk = (lane < nv) && (my_end > my_lo);
         if (walk) {
-            const uint4 nn = *reinterpret_cast<const uint4*>(&s.tile[lane][0]);
-            nb4[0] = nn.x; nb4[1] = nn.y; nb4[2] = nn.z; nb4[3] = nn.w;
+            if constexpr (NIBBLE) {
+                const uint2 nn = *reinterpret_cast<const uint2*>(&s.tile[lane][0]);
+                nb4[0] = nn.x; nb4[1] = nn.y;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)j;
+                for (int j = 0; j < 8; ++j)
+                    if (j < k) {
+                        const u32 v = (nb4[j >> 2] >> (8 * (j & 3))) & 63u;
+                        const u32 sh = (v & 1u) * 4u;
+                        lrow[v >> 1] = (unsigned char)((lrow[v >> 1] & ~(0xFu << sh)) | ((u32)j << sh));
+                    }
+            } else {
+                const uint4 nn = *reinterpret_cast<const uint4*>(&s.tile[lane][0]);
+                nb4[0] = nn.x; nb4[1] = nn.y; nb4[2] = nn.z; nb4[3] = nn.w;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)j;
+            }
         }
         // balanced sub-batches: when the tile does not fit the staging buffer, aim for equal shares
         const int tile_total = (int)min(tile_end - tile_lo, (i64)0x7fffffff);
-        const int nsplit = (tile_total + EMIT_STAGE - 1) / EMIT_STAGE;
-        const int cap_eff = (nsplit <= 1) ? EMIT_STAGE : min(EMIT_STAGE, tile_total / nsplit + 48);
+        const int nsplit = (tile_total + STAGE_N - 1) / STAGE_N;
+        const int cap_eff = (nsplit <= 1) ? STAGE_N : min(STAGE_N, tile_total / nsplit + 48);
         int sa = 0;
         while (sa < nv) {
             const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
@@ -568,10 +630,16 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                     asm volatile("" ::: "memory");  // keep the two blocks in one loop (no loop nesting by the compiler)
                     if (p != pe) {
                         const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
-                        const u32 l = lrow[e & 63u];
-                        if (l != 0xFFu) {
-                            if (NARROW) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
-                            else *st++ = (stage_t)(((e & 0xFFC0u) << 9) + (l << 5) + pj);
+                        if constexpr (NIBBLE) {
+                            const u32 x = e & 63u;
+                            const u32 l = ((u32)lrow[x >> 1] >> ((x & 1u) * 4u)) & 0xFu;
+                            if (l != 0xFu) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
+                        } else {
+                            const u32 l = lrow[e & 63u];
+                            if (l != 0xFFu) {
+                                if (NARROW) *st++ = (stage_t)((e & 0xFFC0u) + (l << 3) + pj);
+                                else *st++ = (stage_t)(((e & 0xFFC0u) << 9) + (l << 5) + pj);
+                            }
                         }
                         p += 2;
                     }
@@ -632,7 +700,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         if (walk) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (j < k) lrow[(nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu] = (unsigned char)0xFF;
+                if (j < k) lrow[((nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu) >> (NIBBLE ? 1 : 0)] = (unsigned char)0xFF;
         }
     }
 }
