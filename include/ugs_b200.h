@@ -138,12 +138,27 @@ int ugs_sort_columns(int64_t E, int64_t G, void* workspace, const ugs_layout* L,
 
 /* Copies counters[0..15] to h_out (16 x int64; synchronises the stream). */
 int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
+/* The same without stalling `stream`: _begin snapshots the counters as of the work queued on `stream` so far (the copy
+ * runs on a library-owned side stream; h_out must be pinned host memory), _end blocks the host until the snapshot has
+ * arrived. Work queued on `stream` between the two calls overlaps the round trip: the drop-in launches the
+ * bitmask-path preprocessing there (UGS_PREPROC_SMALL) while it waits for the segmentation flags / class counts. */
+int ugs_batch_info_begin(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
+int ugs_batch_info_end(void);
 
 /* A.2-A.5 -- per-graph CSR (multigraph, column order), (degree,id) order, suffix degrees, reachability,
  * bucket weights, root CDF. n_general / max_n_general come from ugs_batch_info. */
 int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
                       int k, const int64_t* perm, int64_t n_general, int64_t n_large, void* workspace,
                       const ugs_layout* L, void* stream);
+/* The same in two parts. UGS_PREPROC_SMALL (warp-per-graph kernel over the bitmask-path graphs) needs nothing from the
+ * host and may be launched before the counters have been read (pass n_general = n_large = 0); UGS_PREPROC_GENERAL
+ * (CTA-per-graph / whole-GPU kernels) needs n_general and n_large. */
+#define UGS_PREPROC_SMALL 1
+#define UGS_PREPROC_GENERAL 2
+#define UGS_PREPROC_ALL 3
+int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
+                            int k, const int64_t* perm, int64_t n_general, int64_t n_large, int parts,
+                            void* workspace, const ugs_layout* L, void* stream);
 
 /* Scratch bytes ugs_sample_batch needs for G*m samples. */
 size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);

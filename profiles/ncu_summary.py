@@ -1,0 +1,24 @@
+"""Selected raw metrics of every kernel in an ncu report as CSV: python profiles/ncu_summary.py <rep> > profiles/rNN_ncu_full_summary.csv"""
+import csv
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+        "smsp__average_warp_latency_issue_stalled_wait.ratio", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h = rows[0]
+idx = [h.index(w) for w in WANT if w in h]
+w = csv.writer(sys.stdout)
+for r in rows:
+    if len(r) == len(h):
+        w.writerow([r[i] for i in idx])

@@ -776,12 +776,52 @@ extern "C" int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_
     return UGS_OK;
 }
 
+// Counters without stalling the stream: the copy runs on a side stream that only waits for the work queued on `stream`
+// BEFORE ugs_batch_info_begin, so kernels launched between begin and end (the speculative bitmask-path preprocessing)
+// keep the GPU busy while the host reads the segmentation flags.
+static cudaStream_t g_side_stream[64];
+static cudaEvent_t g_side_event[64];
+static bool g_side_ready[64];
+
+extern "C" int ugs_batch_info_begin(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream_) {
+    if (!workspace || !L || !h_out) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    int dev = 0;
+    UGS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return ugs_set_error(UGS_ELIMIT, "device index %d", dev);
+    if (!g_side_ready[dev]) {
+        UGS_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking));
+        UGS_CUDA_CHECK(cudaEventCreateWithFlags(&g_side_event[dev], cudaEventDisableTiming));
+        g_side_ready[dev] = true;
+    }
+    UGS_CUDA_CHECK(cudaEventRecord(g_side_event[dev], (cudaStream_t)stream_));
+    UGS_CUDA_CHECK(cudaStreamWaitEvent(g_side_stream[dev], g_side_event[dev], 0));
+    UGS_CUDA_CHECK(cudaMemcpyAsync(h_out, (const char*)workspace + L->counters, sizeof(i64) * 16,
+                                   cudaMemcpyDeviceToHost, g_side_stream[dev]));
+    return UGS_OK;
+}
+
+extern "C" int ugs_batch_info_end(void) {
+    int dev = 0;
+    UGS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !g_side_ready[dev]) return ugs_set_error(UGS_EINVAL, "ugs_batch_info_end without begin");
+    UGS_CUDA_CHECK(cudaStreamSynchronize(g_side_stream[dev]));
+    return UGS_OK;
+}
+
 int ugs_launch_preproc_large(const i64* row0, const i64* row1, const i64* ptr, i64 node_base, int k, const i64* perm,
                              i64 n_large, WS& w, cudaStream_t st);  // ugs_preproc_large.cu
 
 extern "C" int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G,
                                  int64_t node_base, int k, const int64_t* perm, int64_t n_general, int64_t n_large,
                                  void* workspace, const ugs_layout* L, void* stream_) {
+    return ugs_preproc_batch_parts(edge_index, E, ptr, G, node_base, k, perm, n_general, n_large, UGS_PREPROC_ALL,
+                                   workspace, L, stream_);
+}
+
+extern "C" int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G,
+                                       int64_t node_base, int k, const int64_t* perm, int64_t n_general,
+                                       int64_t n_large, int parts, void* workspace, const ugs_layout* L,
+                                       void* stream_) {
     if (!workspace || !L) return ugs_set_error(UGS_EINVAL, "NULL workspace/layout");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
     if (G <= 0) return UGS_OK;
@@ -789,12 +829,13 @@ extern "C" int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int
     WS w = ws_views(workspace, L);
     const int64_t* row0 = edge_index;
     const int64_t* row1 = edge_index ? edge_index + E : nullptr;
-    if (n_general < G) {
+    if ((parts & UGS_PREPROC_SMALL) && n_general < G) {
         constexpr int WARPS = 8;
         k_preproc_small<WARPS><<<(unsigned)((G + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(
             row0, row1, ptr, G, node_base, k, perm, w);
         UGS_LAUNCH_CHECK("k_preproc_small");
     }
+    if (!(parts & UGS_PREPROC_GENERAL)) return UGS_OK;
     if (n_large > 0) {
         const int rc = ugs_launch_preproc_large(row0, row1, ptr, node_base, k, perm, n_large, w, st);
         if (rc != UGS_OK) return rc;

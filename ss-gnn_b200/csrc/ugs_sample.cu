@@ -459,8 +459,9 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
 // word in shared memory at the sample's final offset, and the warp then flushes the staged run with fully
 // coalesced 8-byte stores (32 consecutive output entries per store instruction).
 // The kernel is bound by shared-memory latency per resident warp, and shared memory per warp bounds the
-// resident warps: for k <= 8 in mode "sample" a staged entry is 16 bits (payload:10 | l:3 | j:3), which
-// brings a warp to 7.0 KB and 32 warps per SM; other modes stage 32 bits (9.6 KB, 24 warps per SM).
+// resident warps: for k <= 8 in mode "sample" a staged entry is 16 bits (payload:10 | l:3 | j:3) and the
+// local-index map holds 4-bit positions, which brings a warp to 5.5 KB and 40 warps per SM (48 registers);
+// other modes stage 32 bits with a byte map (9.6 KB, 24 warps per SM).
 // (Tried and measured slower, see profiles/README.md: 8 lanes per CSR row with ballot compaction; membership
 // and local index from registers instead of lmap[]; two entries per walk step; per-lane node loads.)
 // =====================================================================================================

@@ -22,6 +22,7 @@ EXPORTS = [
     "ugs_enum_scratch_bytes", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
     "ugs_wl_hash", "ugs_wl_lookup",
+    "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
 ]
 
 
@@ -107,6 +108,9 @@ def lib():
                                      vp, vp, vp, vp, vp, vp]
     L.ugs_wl_hash.argtypes = [vp, i64, ci, vp, i64, vp, ci, vp, vp, vp]
     L.ugs_wl_lookup.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp]
+    L.ugs_batch_info_begin.argtypes = [vp, LP, vp, vp]
+    L.ugs_batch_info_end.argtypes = []
+    L.ugs_preproc_batch_parts.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, ci, vp, LP, vp]
     _LIB = L
     return L
 

@@ -73,16 +73,29 @@ class DeviceBatch:
         self._fast = fast
         with torch.cuda.device(self.device):
             self._segment(fast)
-            info = self.info()
+            speculative = False
+            if fast:
+                # The bitmask-path preprocessing needs nothing from the host: queue it now and read the segmentation
+                # flags / class counts through the side stream while it runs (no GPU idle time for this round trip).
+                _lib.check(L.ugs_batch_info_begin(_ptr(self.ws), ctypes.byref(self.layout),
+                                                  ctypes.c_void_p(self._info_host.data_ptr()), _stream()))
+                self._preproc(0, 0, 1)
+                _lib.check(L.ugs_batch_info_end())
+                info = [int(x) for x in self._info_host.tolist()]
+                speculative = True
+            else:
+                info = self.info()
             if info[CTR["unsorted"]] & 2:
                 raise RuntimeError("ptr must be non-decreasing")
             if fast and (info[CTR["unsorted"]] & 4):
                 self._fast = fast = False
+                speculative = False
                 self._segment(False)
                 info = self.info()
             if info[CTR["unsorted"]] & 1:
                 # Columns are not graph-contiguous (never the case for PyG batches): order them stably by
                 # graph id once and read them through `perm` from here on.
+                speculative = False
                 sb = int(L.ugs_sort_scratch_bytes(self.E))
                 scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
                 self.perm = torch.empty(self.E, dtype=torch.int64, device=self.device)
@@ -95,12 +108,15 @@ class DeviceBatch:
             self.max_n_general = int(info[CTR["max_n_general"]])
             self.n_skipped = int(info[CTR["n_skipped"]])
             self.n_large = int(info[CTR["n_large"]])
-            _lib.check(L.ugs_preproc_batch(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G, self.node_base,
-                                           self.k, _ptr(self.perm), self.n_general, self.n_large, _ptr(self.ws),
-                                           ctypes.byref(self.layout), _stream()))
+            self._preproc(self.n_general, self.n_large, 2 if speculative else 3)
             if self.variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
                 _lib.check(L.ugs_preproc_uniform(_ptr(self.ptr), self.G, self.node_base, self.k, self.n_general,
                                                  _ptr(self.ws), ctypes.byref(self.layout), _stream()))
+
+    def _preproc(self, n_general: int, n_large: int, parts: int):
+        _lib.check(_lib.lib().ugs_preproc_batch_parts(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G,
+                                                      self.node_base, self.k, _ptr(self.perm), n_general, n_large,
+                                                      parts, _ptr(self.ws), ctypes.byref(self.layout), _stream()))
 
     def _late_check(self, info) -> bool:
         """True if the preprocessing kernels found a column outside its graph's range (the fast segmentation was
