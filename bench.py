@@ -335,7 +335,7 @@ def main():
     if not args.no_e2e:
         h_ei = torch.from_numpy(ei_np).pin_memory()
         h_ptr = torch.from_numpy(ptr_np).pin_memory()
-        d2h = 0
+        d2h = delivered = 0
         for w in range(2):
             outs = ugs_sampler.sample_batch(h_ei, h_ptr, m, k, mode="sample", seed=7 + w)
         barrier()
@@ -347,15 +347,18 @@ def main():
             bq.record()
             bq.synchronize()
             tt.append(a.elapsed_time(bq))
-            d2h = sum(o.numel() * o.element_size() for o in outs)
-            assert not outs[0].is_cuda
+            delivered = sum(o.numel() * o.element_size() for o in outs)  # int64 bytes handed to the caller
+            d2h = int(getattr(ugs_sampler._to_host_batch, "last_d2h_bytes", 0)) or delivered  # bytes that crossed PCIe
+            assert not outs[0].is_cuda and outs[0].is_pinned()
         barrier()
         te = torch.tensor([sum(tt) / 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": graphlets_step_all * args.e2e_steps / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h_ei.numel() * 8 + h_ptr.numel() * 8), "d2h_bytes_per_step": int(d2h),
-               "steps": args.e2e_steps, "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu tensors"}
+               "host_bytes_delivered_per_step": int(delivered), "steps": args.e2e_steps,
+               "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu int64 tensors; results cross PCIe packed "
+                      "(int32 / one byte per edge entry) and are widened by host threads while the copy runs"}
         del outs
 
     if rank == 0:

@@ -358,6 +358,9 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
 
 // =====================================================================================================
 // In-place inclusive scan of the per-sample counts (single pass, decoupled look-back)
+// (Fusing this scan into k_sample_small -- CTAs in ticket order publishing their totals and looking back -- was
+// measured slower on B200: 470 us against 321 + 46 us. A sampling CTA lives ~12 us and ~600 of them finish together,
+// so every CTA walks a long look-back window while it still holds its SM slot.)
 // =====================================================================================================
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 16

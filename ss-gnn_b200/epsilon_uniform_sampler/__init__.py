@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 
 from ugs_b200 import engine as _engine
-from ugs_sampler import _device, _to_host
+from ugs_sampler import _device, _to_host_batch
 
 
 def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, k: int, mode: str = "sample",
@@ -33,7 +33,7 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
         b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0])
         outs, stats = b.sample_epsilon(int(m_per_graph), int(k), mode, int(seed), float(epsilon))
         sample_batch.last_stats = stats
-        return tuple(outs if edge_index.is_cuda else _to_host(outs))
+        return tuple(outs if edge_index.is_cuda else _to_host_batch(outs, mode, int(k)))
 
 
 sample_batch.last_stats = None

@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -23,6 +23,7 @@ EXPORTS = [
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
     "ugs_wl_hash", "ugs_wl_lookup",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
+    "ugs_wire_bytes", "ugs_pack_outputs", "ugs_fetch_outputs",
 ]
 
 
@@ -111,6 +112,10 @@ def lib():
     L.ugs_batch_info_begin.argtypes = [vp, LP, vp, vp]
     L.ugs_batch_info_end.argtypes = []
     L.ugs_preproc_batch_parts.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, ci, vp, LP, vp]
+    L.ugs_wire_bytes.restype = sz
+    L.ugs_wire_bytes.argtypes = [i64, ci, i64, ci]
+    L.ugs_pack_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, vp, vp]
+    L.ugs_fetch_outputs.argtypes = [vp, vp, i64, ci, i64, ci, vp, vp, vp, ci, vp]
     _LIB = L
     return L
 

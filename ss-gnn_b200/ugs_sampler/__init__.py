@@ -64,6 +64,60 @@ def _to_host(tensors):
     return out
 
 
+_PACKED_MIN_BYTES = 32 << 20  # below this a plain copy is as fast
+
+
+def _host_threads() -> int:
+    try:
+        return max(1, int(os.environ.get("UGS_B200_HOST_THREADS", "0"))) if os.environ.get("UGS_B200_HOST_THREADS") \
+            else max(1, min(32, os.cpu_count() or 1))
+    except ValueError:
+        return 1
+
+
+def _to_host_batch(outs, mode: str, k: int):
+    """The 5-tuple (nodes, edge_index, edge_ptr, sample_ptr, edge_src) as CPU pinned int64 tensors (the reference's
+    output contract). Large results travel packed (int32 / one byte per edge entry) and are widened into the final
+    tensors by host threads while the transfer is still running (csrc/ugs_hostio.cu); set UGS_B200_PACKED_D2H=0 to
+    force the plain int64 copy."""
+    import ctypes
+    from ugs_b200 import _lib
+    from ugs_b200.engine import _ptr, _stream
+    nodes, eidx, eptr, sptr, esrc = outs
+    nbytes = 8 * (nodes.numel() + eidx.numel() + esrc.numel())
+    _to_host_batch.last_d2h_bytes = nbytes + 8 * (eptr.numel() + sptr.numel())  # what crossed PCIe for this call
+    if nbytes < _PACKED_MIN_BYTES or os.environ.get("UGS_B200_PACKED_D2H", "1") == "0":
+        return _to_host(outs)
+    L = _lib.lib()
+    B, kk, total = int(nodes.shape[0]), int(nodes.shape[1]), int(esrc.numel())
+    pairs = 1 if (mode == "sample" and int(k) <= 16) else 0
+    dev = nodes.device
+    with torch.cuda.device(dev):
+        wb = int(L.ugs_wire_bytes(B, kk, total, pairs))
+        d_wire = torch.empty(wb, dtype=torch.uint8, device=dev)
+        h_wire = torch.empty(wb, dtype=torch.uint8, pin_memory=True)
+        h_nodes = torch.empty(nodes.shape, dtype=torch.int64, pin_memory=True)
+        h_eidx = torch.empty(eidx.shape, dtype=torch.int64, pin_memory=True)
+        h_esrc = torch.empty(esrc.shape, dtype=torch.int64, pin_memory=True)
+        h_eptr = torch.empty(eptr.shape, dtype=torch.int64, pin_memory=True)
+        h_sptr = torch.empty(sptr.shape, dtype=torch.int64, pin_memory=True)
+        _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx.contiguous()), _ptr(esrc), total, pairs,
+                                      _ptr(d_wire), _stream()))
+        h_eptr.copy_(eptr, non_blocking=True)
+        h_sptr.copy_(sptr, non_blocking=True)
+        rc = L.ugs_fetch_outputs(_ptr(d_wire), ctypes.c_void_p(h_wire.data_ptr()), B, kk, total, pairs,
+                                 ctypes.c_void_p(h_nodes.data_ptr()), ctypes.c_void_p(h_eidx.data_ptr()),
+                                 ctypes.c_void_p(h_esrc.data_ptr()), _host_threads(), _stream())
+        torch.cuda.current_stream().synchronize()
+        if rc != 0:  # a value outside the packed ranges (never for valid sampler output): plain copy
+            return _to_host(outs)
+    _to_host_batch.last_d2h_bytes = wb + 8 * (eptr.numel() + sptr.numel())
+    return [h_nodes, h_eidx, h_eptr, h_sptr, h_esrc]
+
+
+_to_host_batch.last_d2h_bytes = 0
+
+
 def _want_cuda_out(inp):
     return inp.is_cuda or os.environ.get("UGS_B200_OUTPUT", "").lower() == "cuda"
 
@@ -154,7 +208,7 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
         b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0], variant=variant)
         outs, _stats = b.sample(int(m_per_graph), int(k), mode, int(seed))
         sample_batch.last_stats = _stats
-        return tuple(outs if _want_cuda_out(edge_index) else _to_host(outs))
+        return tuple(outs if _want_cuda_out(edge_index) else _to_host_batch(outs, mode, int(k)))
 
 
 sample_batch.last_stats = None

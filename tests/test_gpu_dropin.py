@@ -9,7 +9,7 @@ import pytest
 import torch
 from scipy.stats import chi2
 
-from helpers import bidir, per_graph_columns
+from helpers import bidir, per_graph_columns, random_batch
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "ugs_golden.npz")
@@ -163,3 +163,33 @@ def test_handle_api_k_quirks_and_errors(cuda_lib):
         ugs_sampler.sample(h, 1, 3)
     with pytest.raises(RuntimeError):
         ugs_sampler.sample_batch(ei, torch.tensor([0, 3]), 2, 33)  # k above the implementation limit
+
+
+@pytest.mark.parametrize("mode", ["sample", "graph", "global"])
+def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
+    """CPU outputs travel packed (int32 / one byte per edge entry) and are widened on the host (csrc/ugs_hostio.cu):
+    bit-identical to the plain int64 copy, still pinned, in every mode, for every sampler that returns the 5-tuple."""
+    import epsilon_uniform_sampler
+    import rwr_sampler
+    import ugs_sampler
+    from ugs_b200 import synth
+    ei, ptr = synth.make_batch("zinc", 3000, seed=2)
+    tei, tptr = torch.from_numpy(ei), torch.from_numpy(ptr)
+    for mod, kw in ((ugs_sampler, {}), (epsilon_uniform_sampler, dict(epsilon=0.5)), (rwr_sampler, {})):
+        monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
+        packed = mod.sample_batch(tei, tptr, 37, 8, mode, 5, **kw)
+        monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+        plain = mod.sample_batch(tei, tptr, 37, 8, mode, 5, **kw)
+        monkeypatch.delenv("UGS_B200_PACKED_D2H")
+        for a, b in zip(packed, plain):
+            assert a.dtype == torch.int64 and a.is_pinned() and not a.is_cuda
+            assert torch.equal(a, b)
+    # odd sizes / a single host thread / k > 16 (two int32 per entry) / empty edge list
+    monkeypatch.setenv("UGS_B200_HOST_THREADS", "1")
+    ei2, ptr2 = random_batch(np.random.default_rng(9), 23, 1, 60, deg=2.5, big=[(3, 200)])
+    for k, m in ((17, 3), (3, 1)):
+        a = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), m, k, mode, 1)
+        monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+        b = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), m, k, mode, 1)
+        monkeypatch.delenv("UGS_B200_PACKED_D2H")
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
