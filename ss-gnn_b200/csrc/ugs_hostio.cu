@@ -5,7 +5,7 @@
 // measured: 120 ms, sixty times the 2 ms the kernels take). Every value fits far fewer bits, so:
 //   device   ugs_pack_outputs   nodes -> int32, edge_src -> int32, edge_index -> one byte (j | l << 4) per entry in
 //                               mode "sample" with k <= 16, else two int32 per entry            (HBM-bound, ~1 ms)
-//   PCIe     the packed "wire" buffer (1.6 GB instead of 6.8 GB) in 32 MB chunks, one event per chunk
+//   PCIe     the packed "wire" buffer (1.6 GB instead of 6.8 GB) in chunks, one event per chunk
 //   host     ugs_fetch_outputs  worker threads widen every chunk into the final pinned int64 tensors as soon as its
 //                               event has fired, with non-temporal stores (no read-for-ownership of the destination;
 //                               measured on the pool's 16-vCPU hosts: 145 GB/s of int64 written from bytes, 90 GB/s
@@ -14,12 +14,24 @@
 // the host. edge_ptr and sample_ptr are small and copied as they are.
 #include <emmintrin.h>
 
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
 #include "ugs_common.cuh"
 
-#define WIRE_CHUNK_BYTES (32ll << 20)
+// Chunk of the wire buffer per event (UGS_B200_WIRE_CHUNK_MB overrides). Measured on B200 hosts: 2 ... 64 MB chunks all
+// give 1.23-1.28e8 graphlets/s end to end -- the path is bound by host memory bandwidth, not by the chunking.
+static long long wire_chunk_bytes() {
+    static long long v = 0;
+    if (!v) {
+        const char* e = getenv("UGS_B200_WIRE_CHUNK_MB");
+        long long mb = e ? atoll(e) : 0;
+        if (mb < 1 || mb > 1024) mb = 32;
+        v = mb << 20;
+    }
+    return v;
+}
 
 __global__ void __launch_bounds__(256)
 k_pack_i32(const i64* __restrict__ src, i32* __restrict__ dst, i64 n, unsigned long long* __restrict__ bad) {
@@ -124,7 +136,7 @@ extern "C" int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, in
     const WireLayout w = wire_layout(B, k, total, pairs_u8);
     std::vector<WireItem> items;
     auto add_region = [&](int kind, size_t off, size_t n, size_t elem, i64* dst, i64* dst2) {
-        const size_t per = (size_t)WIRE_CHUNK_BYTES / elem;
+        const size_t per = (size_t)wire_chunk_bytes() / elem;
         for (size_t a = 0; a < n; a += per) {
             WireItem it;
             it.kind = kind; it.off = off + a * elem; it.n = (n - a < per) ? n - a : per;

@@ -68,11 +68,15 @@ _PACKED_MIN_BYTES = 32 << 20  # below this a plain copy is as fast
 
 
 def _host_threads() -> int:
+    """Host threads that widen packed results: UGS_B200_HOST_THREADS, else the cores this rank can claim (the box's
+    cores divided by the ranks torchrun started on it), at most 32."""
     try:
-        return max(1, int(os.environ.get("UGS_B200_HOST_THREADS", "0"))) if os.environ.get("UGS_B200_HOST_THREADS") \
-            else max(1, min(32, os.cpu_count() or 1))
+        if os.environ.get("UGS_B200_HOST_THREADS"):
+            return max(1, int(os.environ["UGS_B200_HOST_THREADS"]))
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
     except ValueError:
         return 1
+    return max(1, min(32, (os.cpu_count() or 1) // local_world))
 
 
 def _to_host_batch(outs, mode: str, k: int):
