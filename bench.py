@@ -61,6 +61,26 @@ class ClockSampler:
         self.th = None
 
     def _run(self):
+        # NVML in process (nvidia_ml_py): forking an nvidia-smi every 100 ms from a rank with gigabytes mapped costs that
+        # rank ~0.5 ms hiccups inside the timed region; the subprocess is only the fallback.
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            getr = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            while not self.stop.is_set():
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                r = int(getr(h))
+                row = [str(self.idx), str(sm), str(mx), "", hex(r)]
+                row += ["Active" if r & bits[nm] else "Not Active"
+                        for nm in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append(row)
+                self.stop.wait(0.05)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -282,22 +302,46 @@ def main():
         clk.__enter__()  # sampled from the warm-up to the end of the e2e leg (the timed regions are milliseconds long)
     for w in range(args.warmup):
         step(100 + w, False)
+    # Allocator warm-up: the size of edge_index / edge_src is data dependent (it changes by ~0.01 % with the seed), and
+    # a step whose output is a few KB larger than every earlier one would pay a cudaMalloc (2-3 ms, seen as a one-off
+    # 4 ms step on one rank of a multi-GPU run). Park blocks with 3 % headroom in torch's caching allocator once.
+    if last.get("total"):
+        pad = [torch.empty(int(2 * last["total"] * 1.03), dtype=torch.int64, device=dev),
+               torch.empty(int(last["total"] * 1.03), dtype=torch.int64, device=dev)]
+        del pad
+    import gc
+    gc.collect()
+    gc.disable()  # no cyclic-GC pause inside the timed region
     launches0 = int(L.ugs_launch_count())
     barrier()
     times = [step(1000 + s, True) for s in range(args.steps)]
     barrier()
     launches = int(L.ugs_launch_count()) - launches0
+    gc.enable()
     t_local = sum(times) / 1e3
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_max = float(t.item())
-    per_rank_ms = [1e3 * t_local / args.steps]
+    # per-rank diagnostics: step time, stage times, the slowest single step, and this rank's SM clock right after the
+    # timed loop (NVML, in process -- no nvidia-smi subprocess per rank)
+    def _nvml_clock(idx):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return -1.0
+    diag = [1e3 * t_local / args.steps] + [sum(stage_ms[kk]) / len(stage_ms[kk]) for kk in ("preproc", "sample", "emit")] \
+        + [max(times), _nvml_clock(local_rank)]
+    per_rank_diag = [diag]
     if world > 1:
-        tl = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        tl = torch.tensor(diag, dtype=torch.float64, device=dev)
         tg = [torch.empty_like(tl) for _ in range(world)]
         dist.all_gather(tg, tl)
-        per_rank_ms = [1e3 * float(x.item()) / args.steps for x in tg]
+        per_rank_diag = [x.tolist() for x in tg]
+    per_rank_ms = [d[0] for d in per_rank_diag]
 
     # the one collective of the design: all-gather of per-rank counts/statistics (never on the sampling path)
     st = last["stats"]
@@ -388,6 +432,8 @@ def main():
             },
             "stage_ms": {kk: sum(v) / len(v) for kk, v in stage_ms.items()},
             "ms_per_step_per_rank": per_rank_ms,
+            "per_rank": [dict(zip(["ms_per_step", "preproc_ms", "sample_ms", "emit_ms", "slowest_step_ms", "sm_mhz_after"],
+                                  [round(v, 4) for v in d])) for d in per_rank_diag],
             "roofline": {"bound": "hbm", "kernel": "k_emit_small (induced-edge emission + compaction)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
