@@ -295,15 +295,20 @@ int ugs_presample_load(const int64_t* s_nodes, const int64_t* s_edge_index, int6
 
 /* ---- Weisfeiler-Lehman graphlet classification ----------------------------------------------
  * Replaces compute_wl_hash + extract_subgraph_from_batch (gps/utils/wl_vocab.py:21-108) and the per-sample loop
- * SubgraphSamplingGNNWithWL._compute_wl_ids (gps/models/ss_gnn_wl.py:210-247) for use_node_features = False.
+ * SubgraphSamplingGNNWithWL._compute_wl_ids (gps/models/ss_gnn_wl.py:210-247).
+ *   ugs_wl_node_attr  use_node_features = True only: attr32_out[v] = first four bytes of md5(row v of x) for every node
+ *                  of the batch (the reference's attribute is md5(features.tobytes()).hexdigest()[:8], wl_vocab.py:45-49).
  *   ugs_wl_hash    digest_out[B][2] = the 16-byte BLAKE2b digest whose hex string is exactly what
  *                  nx.weisfeiler_lehman_graph_hash(G, node_attr = str(degree), iterations) returns for the sample's
  *                  nx.Graph (memory order = hex order); num_nodes_out[B] = #(row entries >= 0), 0 = "unknown id".
+ *                  node_attr32 (NULL = degree attributes): per batch node, from ugs_wl_node_attr; n_attr = its length.
  *                  edge_index_s: the sampler's mode-"sample" output [2,total] (row 1 at +total). k <= 16.
  *   ugs_wl_lookup  ids_out[s] = vocab_ids[i] where vocab_keys[i] (two big-endian uint64 per hash, sorted ascending =
  *                  hex-string order) equals digest s; unknown_id when absent or num_nodes == 0 (hash_to_id, :206-217). */
+int ugs_wl_node_attr(const void* x, int64_t n_rows, int64_t row_bytes, uint32_t* attr32_out, void* stream);
 int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index_s, int64_t total,
-                const int64_t* edge_ptr, int iterations, uint64_t* digest_out, int32_t* num_nodes_out, void* stream);
+                const int64_t* edge_ptr, int iterations, const uint32_t* node_attr32, int64_t n_attr,
+                uint64_t* digest_out, int32_t* num_nodes_out, void* stream);
 int ugs_wl_lookup(const uint64_t* digest, const int32_t* num_nodes, int64_t B, const uint64_t* vocab_keys,
                   const int64_t* vocab_ids, int64_t V, int64_t unknown_id, int64_t* ids_out, void* stream);
 

@@ -18,9 +18,16 @@ def _h(label: str) -> str:
     return blake2b(label.encode("ascii"), digest_size=16).hexdigest()
 
 
-def compute_wl_hash(edges, num_nodes: int, num_iterations: int = 3) -> str:
+def node_attr(row_bytes: bytes) -> str:
+    """wl_vocab.py:45-49: hashlib.md5(node_features[i].cpu().numpy().tobytes()).hexdigest()[:8]."""
+    from hashlib import md5
+    return md5(row_bytes).hexdigest()[:8]
+
+
+def compute_wl_hash(edges, num_nodes: int, num_iterations: int = 3, attrs=None) -> str:
     """edges: iterable of (u, v) local ids. nx.Graph semantics: undirected, parallel edges merge, a self loop makes
-    the node its own neighbour once and adds 2 to its degree."""
+    the node its own neighbour once and adds 2 to its degree. attrs: per-node attribute strings (use_node_features)
+    or None for the degree attribute."""
     if num_iterations <= 0:
         raise ValueError("The WL algorithm requires that `iterations` be positive")
     nbrs = [set() for _ in range(num_nodes)]
@@ -28,7 +35,7 @@ def compute_wl_hash(edges, num_nodes: int, num_iterations: int = 3) -> str:
         u, v = int(u), int(v)
         nbrs[u].add(v)
         nbrs[v].add(u)
-    labels = [str(len(nb - {i}) + (2 if i in nb else 0)) for i, nb in enumerate(nbrs)]
+    labels = list(attrs) if attrs is not None else [str(len(nb - {i}) + (2 if i in nb else 0)) for i, nb in enumerate(nbrs)]
     counts = []
     for _ in range(num_iterations):
         labels = [_h(labels[i] + "".join(sorted(labels[j] for j in nbrs[i]))) for i in range(num_nodes)]
@@ -36,14 +43,17 @@ def compute_wl_hash(edges, num_nodes: int, num_iterations: int = 3) -> str:
     return _h(str(tuple(counts)))
 
 
-def batch_hashes(nodes, edge_index, edge_ptr, num_iterations: int = 3):
-    """Per sample: extract_subgraph_from_batch (wl_vocab.py:70-108) + compute_wl_hash; None when no valid node."""
+def batch_hashes(nodes, edge_index, edge_ptr, num_iterations: int = 3, x=None):
+    """Per sample: extract_subgraph_from_batch (wl_vocab.py:70-108) + compute_wl_hash; None when no valid node.
+    x: numpy feature matrix of the batch (use_node_features=True) or None."""
     out = []
     for s in range(nodes.shape[0]):
-        nn = int((nodes[s] >= 0).sum())
+        valid = nodes[s][nodes[s] >= 0]
+        nn = len(valid)
         if nn == 0:
             out.append(None)
             continue
         a, b = int(edge_ptr[s]), int(edge_ptr[s + 1])
-        out.append(compute_wl_hash(zip(edge_index[0, a:b], edge_index[1, a:b]), nn, num_iterations))
+        attrs = [node_attr(x[int(v)].tobytes()) for v in valid] if x is not None else None
+        out.append(compute_wl_hash(zip(edge_index[0, a:b], edge_index[1, a:b]), nn, num_iterations, attrs))
     return out

@@ -10,7 +10,7 @@
 // The output is the SAME hash NetworkX prints (its 16-byte BLAKE2b digest; the host turns it into the hex string), so
 // vocabularies pickled by the reference keep working. NetworkX's algorithm (graph_hashing.py, node_attr given):
 //   label_0(v) = str(deg v)   (nx.Graph: parallel entries merge, a self loop adds 2 to the degree and makes v its own
-//                              neighbour once)
+//                              neighbour once), or, with use_node_features, md5(feature row bytes).hexdigest()[:8]
 //   label_{t+1}(v) = hex(blake2b_16(label_t(v) + "".join(sorted(label_t(u) for u in N(v)))))
 //   after every iteration the sorted (label, count) pairs are appended to a list; the hash is
 //   hex(blake2b_16(str(tuple(list)))), Python's tuple repr: "(('ab..', 2), ('cd..', 1))", "(x,)" for one element.
@@ -126,9 +126,70 @@ __device__ __forceinline__ int lab_cmp(const unsigned char* a, int la, const uns
     return la == lb ? 0 : (la < lb ? -1 : 1);
 }
 
+// ---- MD5 of every feature row: the node attribute when use_node_features = True (wl_vocab.py:45-49:
+//      hashlib.md5(node_features[i].numpy().tobytes()).hexdigest()[:8] -> the first four digest bytes) ------------------
+__device__ __forceinline__ u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__device__ void md5_block(u32* h, const unsigned char* blk) {
+    const u32 K[64] = {
+        0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u,
+        0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u,
+        0xf61e2562u, 0xc040b340u, 0x265e5a51u, 0xe9b6c7aau, 0xd62f105du, 0x02441453u, 0xd8a1e681u, 0xe7d3fbc8u,
+        0x21e1cde6u, 0xc33707d6u, 0xf4d50d87u, 0x455a14edu, 0xa9e3e905u, 0xfcefa3f8u, 0x676f02d9u, 0x8d2a4c8au,
+        0xfffa3942u, 0x8771f681u, 0x6d9d6122u, 0xfde5380cu, 0xa4beea44u, 0x4bdecfa9u, 0xf6bb4b60u, 0xbebfbc70u,
+        0x289b7ec6u, 0xeaa127fau, 0xd4ef3085u, 0x04881d05u, 0xd9d4d039u, 0xe6db99e5u, 0x1fa27cf8u, 0xc4ac5665u,
+        0xf4292244u, 0x432aff97u, 0xab9423a7u, 0xfc93a039u, 0x655b59c3u, 0x8f0ccc92u, 0xffeff47du, 0x85845dd1u,
+        0x6fa87e4fu, 0xfe2ce6e0u, 0xa3014314u, 0x4e0811a1u, 0xf7537e82u, 0xbd3af235u, 0x2ad7d2bbu, 0xeb86d391u};
+    const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9, 14, 20,
+                       5, 9, 14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21,
+                       6, 10, 15, 21, 6, 10, 15, 21};
+    u32 M[16];
+    for (int i = 0; i < 16; ++i)
+        M[i] = (u32)blk[4 * i] | ((u32)blk[4 * i + 1] << 8) | ((u32)blk[4 * i + 2] << 16) | ((u32)blk[4 * i + 3] << 24);
+    u32 a = h[0], b = h[1], c = h[2], d = h[3];
+    for (int i = 0; i < 64; ++i) {
+        u32 f; int g;
+        if (i < 16) { f = (b & c) | (~b & d); g = i; }
+        else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+        else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+        else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+        const u32 t = d;
+        d = c; c = b;
+        b = b + rotl32(a + f + K[i] + M[g], S[i]);
+        a = t;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+}
+
+// attr32[v] = first four bytes of md5(row v) (memory order: byte 0 in the low bits), one thread per row
+__global__ void __launch_bounds__(128)
+k_md5_rows(const unsigned char* __restrict__ x, i64 n_rows, i64 row_bytes, u32* __restrict__ attr32) {
+    const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_rows) return;
+    const unsigned char* p = x + v * row_bytes;
+    u32 h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    unsigned char blk[64];
+    i64 off = 0;
+    for (; off + 64 <= row_bytes; off += 64) {
+        for (int i = 0; i < 64; ++i) blk[i] = p[off + i];
+        md5_block(h, blk);
+    }
+    const int rem = (int)(row_bytes - off);
+    for (int i = 0; i < 64; ++i) blk[i] = (i < rem) ? p[off + i] : (i == rem ? 0x80 : 0);
+    if (rem >= 56) {
+        md5_block(h, blk);
+        for (int i = 0; i < 64; ++i) blk[i] = 0;
+    }
+    const u64 bits = (u64)row_bytes * 8ull;
+    for (int i = 0; i < 8; ++i) blk[56 + i] = (unsigned char)(bits >> (8 * i));
+    md5_block(h, blk);
+    attr32[v] = h[0];
+}
+
 __global__ void __launch_bounds__(128)
 k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ ei_u, const i64* __restrict__ ei_v,
-          const i64* __restrict__ edge_ptr, int iterations, u64* __restrict__ digest_out, i32* __restrict__ num_nodes_out) {
+          const i64* __restrict__ edge_ptr, int iterations, const u32* __restrict__ attr32, i64 n_attr,
+          u64* __restrict__ digest_out, i32* __restrict__ num_nodes_out) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < B; s += stride) {
         int nn = 0;
@@ -144,9 +205,25 @@ k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ e
         }
         unsigned char lab[2][WL_MAX_K][WL_LAB];
         unsigned char len[2][WL_MAX_K];
-        for (int v = 0; v < nn; ++v) {  // attr = str(G.degree(v)); a self loop counts twice
-            const unsigned deg = (unsigned)__popc(adj[v] & ~(1u << v)) + (((adj[v] >> v) & 1u) ? 2u : 0u);
-            len[0][v] = (unsigned char)put_dec(lab[0][v], deg);
+        if (attr32) {  // attr = md5(feature row of the v-th VALID node).hexdigest()[:8]   (wl_vocab.py:45-49,99-103)
+            int v = 0;
+            for (int j = 0; j < k && v < nn; ++j) {
+                const i64 id = nodes[s * k + j];
+                if (id < 0) continue;
+                const u32 a = (id < n_attr) ? attr32[id] : 0u;
+                const char* hx = "0123456789abcdef";
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned byte = (a >> (8 * b)) & 0xFFu;
+                    lab[0][v][2 * b] = hx[byte >> 4]; lab[0][v][2 * b + 1] = hx[byte & 15];
+                }
+                len[0][v] = 8;
+                ++v;
+            }
+        } else {
+            for (int v = 0; v < nn; ++v) {  // attr = str(G.degree(v)); a self loop counts twice
+                const unsigned deg = (unsigned)__popc(adj[v] & ~(1u << v)) + (((adj[v] >> v) & 1u) ? 2u : 0u);
+                len[0][v] = (unsigned char)put_dec(lab[0][v], deg);
+            }
         }
         B2b F;  // the hash of str(tuple(subgraph_hash_counts)), fed as the string is produced
         b2b_init(F);
@@ -234,9 +311,19 @@ k_wl_lookup(const u64* __restrict__ digest, const i32* __restrict__ num_nodes, i
     ids_out[s] = id;
 }
 
+extern "C" int ugs_wl_node_attr(const void* x, int64_t n_rows, int64_t row_bytes, uint32_t* attr32_out, void* stream_) {
+    if (n_rows < 0 || row_bytes < 0) return ugs_set_error(UGS_EINVAL, "negative size");
+    if (n_rows == 0) return UGS_OK;
+    if (!attr32_out || (!x && row_bytes > 0)) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    k_md5_rows<<<(unsigned)((n_rows + 127) / 128), 128, 0, (cudaStream_t)stream_>>>((const unsigned char*)x, n_rows,
+                                                                                  row_bytes, attr32_out);
+    UGS_LAUNCH_CHECK("k_md5_rows");
+    return UGS_OK;
+}
+
 extern "C" int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index_s, int64_t total,
-                           const int64_t* edge_ptr, int iterations, uint64_t* digest_out, int32_t* num_nodes_out,
-                           void* stream_) {
+                           const int64_t* edge_ptr, int iterations, const uint32_t* node_attr32, int64_t n_attr,
+                           uint64_t* digest_out, int32_t* num_nodes_out, void* stream_) {
     if (B < 0 || total < 0) return ugs_set_error(UGS_EINVAL, "negative size");
     if (k < 1 || k > WL_MAX_K) return ugs_set_error(UGS_ELIMIT, "WL hashing supports k in [1, %d]", WL_MAX_K);
     if (iterations <= 0) return ugs_set_error(UGS_EINVAL, "The WL algorithm requires that `iterations` be positive");
@@ -250,7 +337,8 @@ extern "C" int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
     k_wl_hash<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(nodes, B, k, edge_index_s, edge_index_s + total, edge_ptr,
-                                                                  iterations, (u64*)digest_out, num_nodes_out);
+                                                                  iterations, node_attr32, n_attr, (u64*)digest_out,
+                                                                  num_nodes_out);
     UGS_LAUNCH_CHECK("k_wl_hash");
     return UGS_OK;
 }

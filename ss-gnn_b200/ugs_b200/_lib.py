@@ -21,7 +21,7 @@ EXPORTS = [
     "ugs_gather_rows", "ugs_encoder_offsets", "ugs_rwr_sample_batch", "ugs_rwr_emit_edges",
     "ugs_enum_scratch_bytes", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
-    "ugs_wl_hash", "ugs_wl_lookup",
+    "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
     "ugs_wire_bytes", "ugs_pack_outputs", "ugs_fetch_outputs",
 ]
@@ -107,7 +107,8 @@ def lib():
     L.ugs_presample_plan.argtypes = [vp, i64, i64, vp, i64, vp, vp, i64, vp, sz, ctypes.POINTER(i64), vp]
     L.ugs_presample_load.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, i64, ci, vp, i64, vp, vp, i64, ci,
                                      vp, vp, vp, vp, vp, vp]
-    L.ugs_wl_hash.argtypes = [vp, i64, ci, vp, i64, vp, ci, vp, vp, vp]
+    L.ugs_wl_hash.argtypes = [vp, i64, ci, vp, i64, vp, ci, vp, i64, vp, vp, vp]
+    L.ugs_wl_node_attr.argtypes = [vp, i64, i64, vp, vp]
     L.ugs_wl_lookup.argtypes = [vp, vp, i64, vp, vp, i64, i64, vp, vp]
     L.ugs_batch_info_begin.argtypes = [vp, LP, vp, vp]
     L.ugs_batch_info_end.argtypes = []

@@ -36,8 +36,18 @@ def main():
     rows = []
     for name, n, edges in cases():
         ei = torch.tensor(edges, dtype=torch.long).t().reshape(2, -1) if edges else torch.zeros((2, 0), dtype=torch.long)
-        rows.append({"name": name, "n": n, "edges": edges,
-                     "hash": {str(it): compute_wl_hash(ei, n, None, it) for it in (1, 2, 3)}})
+        row = {"name": name, "n": n, "edges": edges,
+               "hash": {str(it): compute_wl_hash(ei, n, None, it) for it in (1, 2, 3)}}
+        # use_node_features=True: float32 feature rows of 1, 7 (28 bytes) and 20 (80 bytes: two md5 blocks) columns and
+        # int64 rows of 7 columns (56 bytes: the md5 padding spills into a second block)
+        g = torch.Generator().manual_seed(len(rows))
+        feats = {"f32x1": torch.randint(0, 5, (n, 1), generator=g).float(),
+                 "f32x7": torch.randn(n, 7, generator=g), "f32x20": torch.randn(n, 20, generator=g),
+                 "i64x7": torch.randint(0, 9, (n, 7), generator=g)}
+        if len(rows) % 3 == 0:  # every third case carries features (keeps the fixture small)
+            row["feat"] = {kk: {"dtype": str(v.dtype).replace("torch.", ""), "values": v.tolist(),
+                                "hash": compute_wl_hash(ei, n, v, 3)} for kk, v in feats.items()}
+        rows.append(row)
     with open(os.path.join(HERE, "wl_golden.json"), "w") as f:
         json.dump(rows, f)
     print("wrote", len(rows), "cases")

@@ -37,6 +37,23 @@ def test_wl_hashes_equal_the_reference_golden(cuda_lib, it):
         assert h == r["hash"][str(it)], (r["name"], it)
 
 
+def test_wl_hashes_with_node_features_equal_the_reference_golden(cuda_lib):
+    """use_node_features=True: md5 of the feature rows on the device (1-, 28-, 56- and 80-byte rows: one md5 block,
+    padding spilling into a second block, two data blocks)."""
+    from ugs_b200 import wl
+    rows = [r for r in json.load(open(GOLD)) if "feat" in r]
+    nodes, ei, eptr = _as_samples(rows, 12)
+    for kk in rows[0]["feat"]:
+        dt = getattr(torch, rows[0]["feat"][kk]["dtype"])
+        ncol = len(rows[0]["feat"][kk]["values"][0])
+        x = torch.zeros((100 * len(rows) + 12, ncol), dtype=dt)
+        for s, r in enumerate(rows):
+            x[100 * s:100 * s + r["n"]] = torch.tensor(r["feat"][kk]["values"], dtype=dt)
+        got = wl.wl_hashes(nodes, ei, eptr, 3, x=x.cuda())
+        for r, h in zip(rows, got):
+            assert h == r["feat"][kk]["hash"], (r["name"], kk)
+
+
 @pytest.mark.parametrize("sampler", ["ugs", "epsilon", "uniform"])
 def test_wl_on_sampler_output_equals_oracle(cuda_lib, sampler):
     """4x-multiplicity UGS entries and one-entry-per-column epsilon/uniform entries give the same nx.Graph."""
@@ -56,6 +73,10 @@ def test_wl_on_sampler_output_equals_oracle(cuda_lib, sampler):
     nodes, eidx, eptr = outs[0], outs[1], outs[2]
     got = wl.wl_hashes(nodes, eidx, eptr, 3)
     want = wo.batch_hashes(nodes.cpu().numpy(), eidx.cpu().numpy(), eptr.cpu().numpy(), 3)
+    assert got == want
+    x = torch.randint(0, 4, (int(ptr[-1]), 3), generator=torch.Generator().manual_seed(1)).float()
+    got = wl.wl_hashes(nodes, eidx, eptr, 2, x=x.cuda())
+    want = wo.batch_hashes(nodes.cpu().numpy(), eidx.cpu().numpy(), eptr.cpu().numpy(), 2, x=x.numpy())
     assert got == want
     assert any(h is None for h in got) or (nodes >= 0).any(dim=1).all()
 

@@ -18,6 +18,18 @@ def test_wl_oracle_matches_reference_golden():
             assert wo.compute_wl_hash(r["edges"], r["n"], it) == r["hash"][str(it)], (r["name"], it)
 
 
+def test_wl_oracle_with_node_features_matches_reference_golden():
+    """use_node_features=True: attribute = md5(feature row bytes).hexdigest()[:8] (wl_vocab.py:45-49)."""
+    from oracle import wl_oracle as wo
+    rows = [r for r in json.load(open(GOLD)) if "feat" in r]
+    assert len(rows) >= 20
+    for r in rows:
+        for kk, f in r["feat"].items():
+            x = np.array(f["values"], dtype=f["dtype"]).reshape(r["n"], -1)
+            attrs = [wo.node_attr(x[i].tobytes()) for i in range(r["n"])]
+            assert wo.compute_wl_hash(r["edges"], r["n"], 3, attrs) == f["hash"], (r["name"], kk)
+
+
 def test_wl_oracle_matches_networkx():
     nx = pytest.importorskip("networkx")
     from oracle import wl_oracle as wo
