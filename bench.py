@@ -285,9 +285,7 @@ def main():
         e2.record()
         nodes, eidx, eptr, sptr, esrc = outs
         total = stats["n_edge_entries"]
-        _lib.check(L.ugs_emit_edges(d_ptr.data_ptr(), G, int(ptr_np[0]), m, k, 0, 0, b.n_general, b.ws.data_ptr(),
-                                    __import__("ctypes").byref(b.layout), nodes.data_ptr(), eptr.data_ptr(), total,
-                                    eidx.data_ptr(), esrc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        b.emit_last("sample")
         e3.record()
         e3.synchronize()
         if timed:

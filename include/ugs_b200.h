@@ -160,7 +160,7 @@ int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, const int64_t*
                             int k, const int64_t* perm, int64_t n_general, int64_t n_large, int parts,
                             void* workspace, const ugs_layout* L, void* stream);
 
-/* Scratch bytes ugs_sample_batch needs for G*m samples. */
+/* Scratch bytes ugs_sample_batch needs for G*m samples (scan status words + one packed row of 8 bytes per sample). */
 size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);
 
 /* A.5-A.6 + counts. Writes nodes[G*m,k] (batch-global ids, -1 pad; lo is added for every mode exactly as the
@@ -186,6 +186,14 @@ int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, 
                    int use_perm, int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
                    const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
                    void* stream);
+
+/* The same when the rows are the ones ugs_sample_batch has just written for the same (G, m, k): sample_scratch is the
+ * scratch buffer of that call. For k <= 8 it holds every row again as eight local-id bytes, so the emission pass reads
+ * 8 instead of 8k bytes per sample (0.47 GB less DRAM traffic per ZINC-shaped step). NULL = read `nodes`. */
+int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode, int use_perm,
+                          int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                          const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                          const void* sample_scratch, size_t sample_scratch_bytes, void* stream);
 
 /* Per-sample induced-edge counts for caller-provided node rows (writes edge_ptr like ugs_sample_batch). */
 int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,

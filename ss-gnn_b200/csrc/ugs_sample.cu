@@ -104,7 +104,7 @@ template <int KT>
 __global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
 k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
                int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
-               i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr) {
+               i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
     __shared__ SmallSamp sm_all[SAMP_WARPS];
     if (KT) k = KT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,6 +129,7 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
             const int nv = (int)min((i64)32, m - (i64)t * 32);
             for (int e = lane; e < nv * k; e += 32) nodes_out[s0 * k + e] = -1;
             if (lane < nv) edge_ptr[1 + s0 + lane] = 0;
+            if (packed && lane < nv) packed[s0 + lane] = ~0ull;
         }
         return;
     }
@@ -172,6 +173,7 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         }
         const i64 s0 = g * m + (i64)t * 32;
         const int nv = (int)min((i64)32, m - (i64)t * 32);
+        if (packed && active) packed[s0 + lane] = nlo;  // the emission pass reads 8 bytes per sample instead of 8k
 #if SAMP_VECSTORE
         if (KT > 0 && KT <= 8 && (KT & 1) == 0) {
             // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-             i64* __restrict__ out_src) {
+             i64* __restrict__ out_src, const u64* __restrict__ packed) {
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     constexpr bool NIBBLE = NARROW && (EMIT_NIBBLE != 0);  // k <= 8: two vertices per lmap byte
     constexpr int STAGE_N = (int)(sizeof(SmallEmit<stage_t>::stage) / sizeof(stage_t));
@@ -568,7 +570,10 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 my_end = (lane == nv - 1 || lane == 31) ? tile_end : my_hi;
         const i64 tile_lo = __shfl_sync(FULL_MASK, my_lo, 0);
         if (tile_end == tile_lo) continue;
-        {   // node rows -> shared tile (coalesced read)
+        // NARROW: the sampling kernel left the row of every sample as eight local-id bytes (8 B instead of 8k B)
+        const bool have_packed = NARROW && (packed != nullptr);
+        const u64 prow = (have_packed && lane < nv) ? packed[s0 + lane] : ~0ull;
+        if (!have_packed) {   // node rows -> shared tile (coalesced read)
             int sidx = lane / k, j = lane - sidx * k;
             const i64* in = nodes + s0 * k;
             for (int e = lane; e < nv * k; e += 32) {
@@ -585,8 +590,11 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const bool walk = (lane < nv) && (my_end > my_lo);
         if (walk) {
             if constexpr (NIBBLE) {
-                const uint2 nn = *reinterpret_cast<const uint2*>(&s.tile[lane][0]);
-                nb4[0] = nn.x; nb4[1] = nn.y;
+                if (have_packed) { nb4[0] = (u32)prow; nb4[1] = (u32)(prow >> 32); }
+                else {
+                    const uint2 nn = *reinterpret_cast<const uint2*>(&s.tile[lane][0]);
+                    nb4[0] = nn.x; nb4[1] = nn.y;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (j < k) {
@@ -783,14 +791,20 @@ static int sm_count() {
     return sms;
 }
 
+// scratch = [scan status words | packed node rows: one u64 (eight local ids, 0xFF = -1) per sample, k <= 8]
+static size_t scan_scratch_bytes(int64_t B) {
+    const int64_t tiles = ((B > 0 ? B : 0) + SCAN_TILE - 1) / SCAN_TILE + 1;
+    return (size_t)(tiles + 1) * sizeof(unsigned long long);
+}
+static size_t packed_rows_offset(int64_t B) { return (scan_scratch_bytes(B) + 255) & ~(size_t)255; }
+
 extern "C" size_t ugs_sample_scratch_bytes(int64_t G, int64_t m) {
     const int64_t B = (G > 0 && m > 0) ? G * m : 0;
-    const int64_t tiles = (B + SCAN_TILE - 1) / SCAN_TILE + 1;
-    return (size_t)(tiles + 1) * sizeof(unsigned long long);
+    return packed_rows_offset(B) + (size_t)B * sizeof(u64);
 }
 
 static int run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& w, cudaStream_t st) {
-    const size_t need = ugs_sample_scratch_bytes(B, 1);
+    const size_t need = scan_scratch_bytes(B);
     if (scratch_bytes < need || !scratch) return ugs_set_error(UGS_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, need);
     UGS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need, st));
     if (B > 0) {
@@ -849,12 +863,16 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
     }
     int tpi; int64_t ipg;
     small_items(m, &tpi, &ipg);
+    // packed node rows for the emission pass (k <= 8), kept behind the scan words of the caller's scratch buffer
+    u64* packed = nullptr;
+    if (k <= 8 && scratch && scratch_bytes >= ugs_sample_scratch_bytes(G, m))
+        packed = reinterpret_cast<u64*>((char*)scratch + packed_rows_offset(G * m));
     {
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
 #define UGS_LAUNCH_SAMPLE(KT_)                                                                                   \
     k_sample_small<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, ibase, \
-                                                            seed_mode, tpi, ipg, w, nodes, edge_ptr, sample_ptr)
+                                                            seed_mode, tpi, ipg, w, nodes, edge_ptr, sample_ptr, packed)
         switch (k) {
             case 3: UGS_LAUNCH_SAMPLE(3); break;
             case 4: UGS_LAUNCH_SAMPLE(4); break;
@@ -913,6 +931,15 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
                               int use_perm, int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
                               const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
                               void* stream_) {
+    return ugs_emit_edges_packed(ptr, G, node_base, m, k, mode, use_perm, n_general, workspace, L, nodes, edge_ptr, total,
+                                 edge_index_out, edge_src_out, nullptr, 0, stream_);
+}
+
+extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode,
+                                     int use_perm, int64_t n_general, const void* workspace, const ugs_layout* L,
+                                     const int64_t* nodes, const int64_t* edge_ptr, int64_t total,
+                                     int64_t* edge_index_out, int64_t* edge_src_out, const void* sample_scratch,
+                                     size_t sample_scratch_bytes, void* stream_) {
     if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (mode < 0 || mode > UGS_MODE_ENCODER) return ugs_set_error(UGS_EINVAL, "mode must be one of: 'sample', 'graph', 'global'");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
@@ -922,6 +949,9 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
     WS w = ws_views(const_cast<void*>(workspace), L);
     i64* out_u = edge_index_out;
     i64* out_v = edge_index_out + total;
+    const u64* packed = nullptr;  // rows as ugs_sample_batch packed them for exactly these (G, m, k <= 8)
+    if (sample_scratch && k <= 8 && sample_scratch_bytes >= ugs_sample_scratch_bytes(G, m))
+        packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
     if (n_general < G) {
         int tpi; int64_t ipg;
         small_items(m, &tpi, &ipg);
@@ -931,12 +961,12 @@ extern "C" int ugs_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, 
             const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out);
+                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out, packed);
         } else {
             const size_t smem = sizeof(SmallEmit<u32>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<false><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out);
+                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out, nullptr);
         }
         UGS_LAUNCH_CHECK("k_emit_small");
     }

@@ -210,11 +210,24 @@ class DeviceBatch:
                          n_general_graphs=self.n_general, n_trials=info[CTR["trials"]])
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            # only the reference-law kernels leave packed rows behind the scan words of `scratch`
+            packed = scratch if variant == "ref" else None
+            self._emit_args = (nodes, edge_ptr, total, m, k, edge_index, edge_src, packed, sbytes)
             if emit:
-                _lib.check(L.ugs_emit_edges(_ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,
-                                            _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr),
-                                            total, _ptr(edge_index), _ptr(edge_src), _stream()))
+                self.emit_last(mode)
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
+
+    def emit_last(self, mode: str = "sample"):
+        """Induced-edge emission for the rows of the last `sample(..., emit=False)` call (bench.py times the two halves
+        separately). Uses the packed rows that call left in its scratch buffer."""
+        nodes, edge_ptr, total, m, k, edge_index, edge_src, scratch, sbytes = self._emit_args
+        G = max(self.G, 0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ugs_emit_edges_packed(
+                _ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,
+                _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes), _ptr(edge_ptr), total, _ptr(edge_index),
+                _ptr(edge_src), _ptr(scratch), sbytes, _stream()))
+        self._emit_args = None
 
     def sample_epsilon(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
                        epsilon: float = 0.1, graph_index_base: int = 0, given_nodes=None):
