@@ -15,6 +15,7 @@
 #include <emmintrin.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -125,6 +126,8 @@ struct WireItem {
 };
 
 static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_fetch_mutex;  // one delivery at a time per process: the event pool is shared and the host threads
+                                  // of two concurrent deliveries would only fight for the same memory bandwidth
 
 extern "C" int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, int k, int64_t total, int pairs_u8,
                                  int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads,
@@ -133,6 +136,7 @@ extern "C" int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, in
     if (!d_wire || !h_wire) return ugs_set_error(UGS_EINVAL, "NULL wire buffer");
     if ((B * k > 0 && !h_nodes) || (total > 0 && (!h_edge_index || !h_edge_src))) return ugs_set_error(UGS_EINVAL, "NULL destination");
     cudaStream_t st = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(g_fetch_mutex);
     const WireLayout w = wire_layout(B, k, total, pairs_u8);
     std::vector<WireItem> items;
     auto add_region = [&](int kind, size_t off, size_t n, size_t elem, i64* dst, i64* dst2) {

@@ -9,6 +9,8 @@
 //   * bitmask path  (n <= 64, <= 384 columns, k <= 16): one WARP per graph, everything in shared memory;
 //   * general path  (anything else, k <= 32): one BLOCK per graph, tables in the global workspace (L2).
 #include <stdio.h>
+#include <mutex>
+
 #include "ugs_common.cuh"
 
 // =====================================================================================================
@@ -782,12 +784,14 @@ extern "C" int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_
 static cudaStream_t g_side_stream[64];
 static cudaEvent_t g_side_event[64];
 static bool g_side_ready[64];
+static std::mutex g_side_mutex;  // ctypes releases the GIL: two Python threads may be inside the library at once
 
 extern "C" int ugs_batch_info_begin(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream_) {
     if (!workspace || !L || !h_out) return ugs_set_error(UGS_EINVAL, "NULL argument");
     int dev = 0;
     UGS_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return ugs_set_error(UGS_ELIMIT, "device index %d", dev);
+    std::lock_guard<std::mutex> lock(g_side_mutex);  // record + wait + copy must not interleave with another caller's
     if (!g_side_ready[dev]) {
         UGS_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side_stream[dev], cudaStreamNonBlocking));
         UGS_CUDA_CHECK(cudaEventCreateWithFlags(&g_side_event[dev], cudaEventDisableTiming));

@@ -193,3 +193,29 @@ def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
         b = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), m, k, mode, 1)
         monkeypatch.delenv("UGS_B200_PACKED_D2H")
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_concurrent_calls_from_python_threads(cuda_lib, monkeypatch):
+    """ctypes releases the GIL, so two Python threads can be inside libugs_b200 at the same time (the reference holds
+    the GIL for the whole call): results must be the ones of the serial calls."""
+    import threading
+    import ugs_sampler
+    from ugs_b200 import synth
+    monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
+    jobs = []
+    for i in range(4):
+        ei, ptr = synth.make_batch("zinc", 800 + 100 * i, seed=20 + i)
+        jobs.append((torch.from_numpy(ei), torch.from_numpy(ptr), 16 + i, 5 + (i % 3), 100 + i))
+    serial = [ugs_sampler.sample_batch(e, p, m, k, "sample", s) for e, p, m, k, s in jobs]
+    got = [None] * len(jobs)
+
+    def run(i):
+        e, p, m, k, s = jobs[i]
+        for _ in range(3):
+            got[i] = ugs_sampler.sample_batch(e, p, m, k, "sample", s)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for a, b in zip(serial, got):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
