@@ -510,7 +510,7 @@ struct __align__(16) SmallEmit<unsigned short> {  // 5664 bytes per warp: 5 CTAs
 // payload = source column relative to the graph's first column (graph-contiguous batches), or the CSR position
 // when the columns are read through `perm` (the source column is then gathered from csr_col at flush time).
 
-// NARROW: k <= 8 and mode "sample": staged entry = payload << 6 | l << 3 | j          (16 bits)
+// NARROW: k <= 8 and mode "sample" / encoder: staged entry = payload << 6 | l << 3 | j  (16 bits)
 // else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
 template <bool NARROW>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
@@ -659,7 +659,33 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
             }
             __syncwarp();
             // ---- flush: entry e of the run goes to global position base + e ------------------------------
-            if (NARROW) {
+            if (NARROW && mode == UGS_MODE_ENCODER) {
+                // batch-level ids (s*k + j, s*k + l): the owning sample of staged entry e is the last lane of the
+                // sub-batch whose first entry is <= e -- a 5-step search over the lanes' start offsets
+                const int rel_lo = (lane >= sa && lane < sb) ? (int)(my_lo - base) : 0x7fffffff;
+                i64* pu = out_u + base + lane;
+                i64* pv = out_v + base + lane;
+                i64* ps = out_src + base + lane;
+                const stage_t* sg = s.stage + lane;
+                for (int e0 = 0; e0 < run; e0 += 32) {
+                    const int e = e0 + lane;
+                    int a = sa;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int cand = a + step;
+                        const int off = __shfl_sync(FULL_MASK, rel_lo, cand & 31);
+                        if (cand < sb && off <= e) a = cand;
+                    }
+                    if (e < run) {
+                        const u32 pk = sg[0];
+                        const i64 ik = (s0 + a) * (i64)k;
+                        pu[0] = ik + (i64)(pk & 7u);
+                        pv[0] = ik + (i64)((pk >> 3) & 7u);
+                        ps[0] = use_perm ? (i64)__ldg(gcol + (pk >> 6)) : c0 + (i64)(pk >> 6);
+                    }
+                    pu += 32; pv += 32; ps += 32; sg += 32;
+                }
+            } else if (NARROW) {
                 i64* pu = out_u + base + lane;
                 i64* pv = out_v + base + lane;
                 i64* ps = out_src + base + lane;
@@ -957,7 +983,7 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
         small_items(m, &tpi, &ipg);
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS);
-        if (k <= 8 && mode == UGS_MODE_SAMPLE) {
+        if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
             const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
