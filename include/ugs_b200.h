@@ -13,17 +13,23 @@
  *   ugs_workspace_layout(E, G, NT, &L)                         host only, sizes the workspace
  *   ugs_segment_batch(...)        A.1  columns -> graphs       replaces slice_and_renumber (:41-75)
  *   ugs_batch_info(...)                host reads {unsorted, n_general, max_n_general, ...}
- *   [ugs_segment_apply_perm(...)]      only when the columns are not graph-contiguous
+ *                                      (or ugs_batch_info_begin / ugs_preproc_batch_parts(SMALL) / ugs_batch_info_end:
+ *                                      the round trip then overlaps the bitmask-path preprocessing)
+ *   [ugs_sort_columns(...) + ugs_segment_batch(perm)]   only when the columns are not graph-contiguous
  *   ugs_preproc_batch(...)        A.2-A.5  CSR, order, suffix degrees, weights
  *                                      replaces create_preproc (preproc.cpp:262-284) per graph
  *   ugs_sample_batch(...)         A.5-A.6  roots + growth + per-sample edge counts + scan
  *                                      replaces sample() (sampler.cpp:91-181) per graph
  *   <host reads *d_total, allocates edge_index[2,Ebar], edge_src[Ebar]>
- *   ugs_emit_edges(...)           A.7  induced-edge extraction + compaction
+ *   ugs_emit_edges[_packed](...)  A.7  induced-edge extraction + compaction
  *                                      replaces sampler.cpp:205-280 and the batch driver's
  *                                      post-processing (ugs_sampler_batch_extension.cpp:188-231)
  *
- * "A.n" refers to SURVEY.md Appendix A (exact semantics).
+ *   [ugs_pack_outputs + ugs_fetch_outputs]   CPU int64 tensors of the reference ABI, packed across PCIe
+ *
+ * The other reference samplers (ugs_eps_*, ugs_apx_*, ugs_rwr_*, ugs_enum_*) share the workspace built by the first
+ * three calls; ugs_gather_rows / ugs_encoder_offsets, ugs_presample_* and ugs_wl_* cover the callers either side of the
+ * sampler (SURVEY.md section 8 f). "A.n" refers to SURVEY.md Appendix A (exact semantics).
  */
 #ifndef UGS_B200_H
 #define UGS_B200_H
