@@ -76,7 +76,7 @@ typedef struct ugs_layout {
     size_t cstart;     /* int64  [G+2]   column range of graph g: [cstart[g], cstart[g+1]) */
     size_t ginfo;      /* ugs_ginfo [G]                                                    */
     size_t glist;      /* int32  [G]     ids of the graphs on the general (warp-per-sample) path */
-    size_t counters;   /* int64  [16]    see UGS_CTR_*                                      */
+    size_t counters;   /* int64  [64]    see UGS_CTR_*                                      */
     size_t colkey;     /* int32  [E]     graph id of each column (G = belongs to no graph)  */
     size_t rowptr;     /* uint32 [NT+G]  graph g: n+1 entries at (lo-node_base)+g, relative to 2*cstart[g] */
     size_t order;      /* int32  [NT]    vertex (local id) at order position vi   (Preproc::order)      */
@@ -115,6 +115,11 @@ typedef struct ugs_ginfo {
 #define UGS_CTR_TRIALS 7        /* growth attempts (== samples for VARIANT_REF)                          */
 #define UGS_CTR_SCAN_TICKET 8
 #define UGS_CTR_N_LARGE 9        /* general-path graphs with more than UGS_LARGE_N nodes                   */
+#define UGS_CTR_COUNT 64         /* int64 words in counters[]                                             */
+#define UGS_CTR_EARLY_TOTAL 16   /* [16, 48): partial sums of the per-sample entry counts, added up by the sampling
+                                    kernels themselves (32 addresses to spread the atomics); their sum is the total
+                                    number of emitted entries, known BEFORE the scan kernel has run          */
+#define UGS_CTR_EARLY_SLOTS 32
 
 int ugs_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (monotonic; for measurement). */
@@ -145,7 +150,7 @@ int ugs_sort_columns(int64_t E, int64_t G, void* workspace, const ugs_layout* L,
 /* Copies counters[0..15] to h_out (16 x int64; synchronises the stream). */
 int ugs_batch_info(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
 /* The same without stalling `stream`: _begin snapshots the counters as of the work queued on `stream` so far (the copy
- * runs on a library-owned side stream; h_out must be pinned host memory), _end blocks the host until the snapshot has
+ * runs on a library-owned side stream; h_out must be pinned host memory of UGS_CTR_COUNT int64), _end blocks the host until the snapshot has
  * arrived. Work queued on `stream` between the two calls overlaps the round trip: the drop-in launches the
  * bitmask-path preprocessing there (UGS_PREPROC_SMALL) while it waits for the segmentation flags / class counts. */
 int ugs_batch_info_begin(const void* workspace, const ugs_layout* L, int64_t* h_out, void* stream);
@@ -165,6 +170,18 @@ int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, 
 int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
                             int k, const int64_t* perm, int64_t n_general, int64_t n_large, int parts,
                             void* workspace, const ugs_layout* L, void* stream);
+
+/* ugs_sample_batch with an early read-back: when h_info (pinned host memory, UGS_CTR_COUNT int64) is not NULL, a
+ * snapshot of counters[] taken after the sampling kernels and BEFORE the scan travels to h_info over the library's side
+ * stream; ugs_batch_info_end() waits for it. The host thereby learns the number of emitted entries
+ * (sum of h_info[UGS_CTR_EARLY_TOTAL .. +UGS_CTR_EARLY_SLOTS)), the incomplete / relaxed counts and the late
+ * segmentation flag while the scan kernel is still running, allocates edge_index / edge_src and queues the emission
+ * pass behind the scan: the data-dependent allocation no longer costs GPU idle time. UGS_VARIANT_REF only. */
+int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                           uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                           int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
+                           void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
+                           int64_t* sample_ptr, int64_t* h_info, void* stream);
 
 /* Scratch bytes ugs_sample_batch needs for G*m samples (scan status words + one packed row of 8 bytes per sample). */
 size_t ugs_sample_scratch_bytes(int64_t G, int64_t m);

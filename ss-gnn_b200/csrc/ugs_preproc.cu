@@ -722,7 +722,7 @@ extern "C" int ugs_workspace_layout(int64_t E, int64_t G, int64_t NT, ugs_layout
     L->cstart = take(sizeof(i64) * (size_t)(G + 2));
     L->ginfo = take(sizeof(ugs_ginfo) * (size_t)(G + 1));
     L->glist = take(sizeof(i32) * (size_t)(G + 1));
-    L->counters = take(sizeof(i64) * 16);
+    L->counters = take(sizeof(i64) * UGS_CTR_COUNT);
     L->colkey = take(sizeof(i32) * (size_t)(E + 1));
     L->rowptr = take(sizeof(u32) * (size_t)(NT + G + 1));
     L->order = take(sizeof(i32) * (size_t)(NT + 1));
@@ -749,7 +749,7 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
     if (k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be <= %d", UGS_MAX_K);
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
-    UGS_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(i64) * 16, st));
+    UGS_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(i64) * UGS_CTR_COUNT, st));
     const int T = 256;
     if (fast && !perm) {
         k_seg_fast<<<(unsigned)((G + 2 + T - 1) / T), T, 0, st>>>(edge_index, E, ptr, G, w.cstart);
@@ -799,7 +799,7 @@ extern "C" int ugs_batch_info_begin(const void* workspace, const ugs_layout* L, 
     }
     UGS_CUDA_CHECK(cudaEventRecord(g_side_event[dev], (cudaStream_t)stream_));
     UGS_CUDA_CHECK(cudaStreamWaitEvent(g_side_stream[dev], g_side_event[dev], 0));
-    UGS_CUDA_CHECK(cudaMemcpyAsync(h_out, (const char*)workspace + L->counters, sizeof(i64) * 16,
+    UGS_CUDA_CHECK(cudaMemcpyAsync(h_out, (const char*)workspace + L->counters, sizeof(i64) * UGS_CTR_COUNT,
                                    cudaMemcpyDeviceToHost, g_side_stream[dev]));
     return UGS_OK;
 }

@@ -161,6 +161,7 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
     const u64 cg = seed_mode ? 0ull : gidx;
     const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
     int n_incomplete = 0;
+    i64 cnt_sum = 0;  // this lane's emitted-entry count over the item's tiles (early total, see UGS_CTR_EARLY_TOTAL)
 
     for (int t = t0; t < t1; ++t) {
         const i64 i = (i64)t * 32 + lane;  // sample index inside the graph
@@ -174,6 +175,7 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         const i64 s0 = g * m + (i64)t * 32;
         const int nv = (int)min((i64)32, m - (i64)t * 32);
         if (packed && active) packed[s0 + lane] = nlo;  // the emission pass reads 8 bytes per sample instead of 8k
+        cnt_sum += cnt;
 #if SAMP_VECSTORE
         if (KT > 0 && KT <= 8 && (KT & 1) == 0) {
             // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
@@ -207,6 +209,10 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
     }
     // statistics (the only cross-rank exchange later all-gathers these)
     n_incomplete = __reduce_add_sync(FULL_MASK, n_incomplete);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cnt_sum += __shfl_xor_sync(FULL_MASK, cnt_sum, off);
+    if (lane == 0 && cnt_sum)
+        atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], (unsigned long long)cnt_sum);
     if (lane == 0) {
         if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
         if (chunk == 0 && gi.level > 0) atomicAdd(&w.counters[UGS_CTR_RELAXED], 1ull);
@@ -237,7 +243,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
     const u32 lt_mask = (1u << lane) - 1u;
     const i64 total = n_general * m;
     const i64 nwarps = (i64)gridDim.x * wpb;
-    unsigned long long n_incomplete = 0, n_relaxed = 0;
+    unsigned long long n_incomplete = 0, n_relaxed = 0, n_entries = 0;
 
     for (i64 t = (i64)blockIdx.x * wpb + warp; t < total; t += nwarps) {
         const i64 gi_ = t / m;
@@ -349,10 +355,12 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
         if (lane == 0) {
             edge_ptr[1 + sidx] = (size == k) ? (i64)cntE : 0;
             if (size < k) n_incomplete++;
+            else n_entries += (unsigned long long)cntE;
         }
         (void)lt_mask;
     }
     if (lane == 0) {
+        if (n_entries) atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], n_entries);
         if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], n_incomplete);
         if (n_relaxed) atomicAdd(&w.counters[UGS_CTR_RELAXED], n_relaxed);
     }
@@ -858,7 +866,18 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
                                 int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L, void* scratch,
                                 size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
                                 void* stream_) {
+    return ugs_sample_batch_early(ptr, G, node_base, m, k, seed, graph_index_base, sample_index_base, seed_mode, variant,
+                                  n_general, max_n_general, workspace, L, scratch, scratch_bytes, nodes, edge_ptr,
+                                  sample_ptr, nullptr, stream_);
+}
+
+extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                                      uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                                      int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
+                                      void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
+                                      int64_t* sample_ptr, int64_t* h_info, void* stream_) {
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    if (h_info && variant != UGS_VARIANT_REF) return ugs_set_error(UGS_EINVAL, "the early read-back needs UGS_VARIANT_REF");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
     if (m < 0) return ugs_set_error(UGS_EINVAL, "m_per_graph must be >= 0");
     if (variant != UGS_VARIANT_REF && variant != UGS_VARIANT_UNIFORM) return ugs_set_error(UGS_EINVAL, "unknown variant %d", variant);
@@ -873,7 +892,12 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
     UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64) * 4, st));
+    UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_EARLY_TOTAL], 0, sizeof(i64) * UGS_CTR_EARLY_SLOTS, st));
     if (G <= 0 || m == 0) {
+        if (h_info) {  // nothing is sampled: the snapshot is all the caller needs
+            const int rc = ugs_batch_info_begin(workspace, L, h_info, stream_);
+            if (rc != UGS_OK) return rc;
+        }
         // sample_ptr = arange * m; edge_ptr = [0]
         UGS_CUDA_CHECK(cudaMemsetAsync(edge_ptr, 0, sizeof(i64), st));
         UGS_CUDA_CHECK(cudaMemsetAsync(sample_ptr, 0, sizeof(i64) * (size_t)((G > 0 ? G : 0) + 1), st));
@@ -927,6 +951,10 @@ extern "C" int ugs_sample_batch(const int64_t* ptr, int64_t G, int64_t node_base
         k_sample_general<<<(unsigned)blocks, wpb * 32, smem, st>>>(ptr, node_base, m, k, seed, graph_index_base, ibase,
                                                                   seed_mode, n_general, bm_words, w, nodes, edge_ptr);
         UGS_LAUNCH_CHECK("k_sample_general");
+    }
+    if (h_info) {  // counters as of the sampling kernels travel to the host while the scan runs
+        const int rc = ugs_batch_info_begin(workspace, L, h_info, stream_);
+        if (rc != UGS_OK) return rc;
     }
     return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
 }

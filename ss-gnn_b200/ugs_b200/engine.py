@@ -57,7 +57,7 @@ class DeviceBatch:
         _lib.check(L.ugs_workspace_layout(self.E, max(self.G, 0), self.NT, ctypes.byref(self.layout)))
         self.ws = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
         self.perm = None
-        self._info_host = torch.empty(16, dtype=torch.int64).pin_memory()
+        self._info_host = torch.empty(64, dtype=torch.int64).pin_memory()  # UGS_CTR_COUNT words
         self._skip_lt_k = skip_lt_k
         self.variant = variant
         if variant not in ("ref", "uniform"):
@@ -81,7 +81,7 @@ class DeviceBatch:
                                                   ctypes.c_void_p(self._info_host.data_ptr()), _stream()))
                 self._preproc(0, 0, 1)
                 _lib.check(L.ugs_batch_info_end())
-                info = [int(x) for x in self._info_host.tolist()]
+                info = [int(x) for x in self._info_host[:16].tolist()]
                 speculative = True
             else:
                 info = self.info()
@@ -136,7 +136,7 @@ class DeviceBatch:
         """counters[0..15] as a list of python ints (synchronises the current stream)."""
         _lib.check(_lib.lib().ugs_batch_info(_ptr(self.ws), ctypes.byref(self.layout),
                                              ctypes.c_void_p(self._info_host.data_ptr()), _stream()))
-        return [int(x) for x in self._info_host.tolist()]
+        return [int(x) for x in self._info_host[:16].tolist()]
 
     # -- typed views into the workspace (parity tests read the deterministic stages through these) --
     _VIEWS = {
@@ -194,13 +194,23 @@ class DeviceBatch:
             sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
             sbytes = int(L.ugs_sample_scratch_bytes(G, m))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.ugs_sample_batch(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
-                                          graph_index_base, int(sample_index_base), 1 if per_graph_seed else 0,
-                                          VARIANTS[variant], self.n_general,
-                                          self.max_n_general,
-                                          _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch), sbytes,
-                                          _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr), _stream()))
-            info = self.info()
+            early = variant == "ref"
+            # reference-law path: the counters travel to the host as soon as the sampling kernels are done, i.e. while the
+            # scan kernel runs, so allocating the data-dependent outputs does not leave the GPU idle
+            _lib.check(L.ugs_sample_batch_early(_ptr(self.ptr), G, self.node_base, m, k, seed & (2 ** 64 - 1),
+                                                graph_index_base, int(sample_index_base), 1 if per_graph_seed else 0,
+                                                VARIANTS[variant], self.n_general, self.max_n_general,
+                                                _ptr(self.ws), ctypes.byref(self.layout), _ptr(scratch), sbytes,
+                                                _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr),
+                                                ctypes.c_void_p(self._info_host.data_ptr()) if early else None,
+                                                _stream()))
+            if early:
+                _lib.check(L.ugs_batch_info_end())
+                raw = self._info_host.tolist()
+                info = [int(x) for x in raw[:16]]
+                info[CTR["total_edges"]] = int(sum(raw[16:48]))  # UGS_CTR_EARLY_TOTAL slots
+            else:
+                info = self.info()
             if self._late_check(info):
                 return self.sample(m, k, mode, seed, graph_index_base, variant, emit, sample_index_base,
                                    per_graph_seed)
