@@ -372,8 +372,12 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
 // measured slower on B200: 470 us against 321 + 46 us. A sampling CTA lives ~12 us and ~600 of them finish together,
 // so every CTA walks a long look-back window while it still holds its SM slot.)
 // =====================================================================================================
+#ifndef SCAN_THREADS
 #define SCAN_THREADS 256
+#endif
+#ifndef SCAN_ITEMS
 #define SCAN_ITEMS 16
+#endif
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 __global__ void __launch_bounds__(SCAN_THREADS)
