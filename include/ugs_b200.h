@@ -286,23 +286,29 @@ int ugs_rwr_emit_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t
                        void* stream);
 
 /* ---- exactly uniform sampler by enumeration (reference src/samplers/uniform_sampler/src/uniform_sampler.cpp:86-282) ---
- * Same workspace as the UGS path (adjacency bitmasks + CSR). Bitmask-path graphs only (n_general must be 0) and
- * k <= 16: the reference itself tests all C(n,k) combinations per graph (:47-81).
+ * Same workspace as the UGS path (adjacency bitmasks + CSR); n_general / max_n_general come from ugs_batch_info.
+ * Graphs with <= 64 vertices are enumerated on 64-bit masks (k <= 16), larger ones (<= 2048 vertices, k <= 8) on
+ * multi-word bitsets; the reference itself tests all C(n,k) combinations per graph (:47-81).
  *   ugs_enum_count         every connected k-subset counted once (ESU recursion); per-root and per-graph counts go to
  *                          enum_scratch, their total to counters[UGS_CTR_TOTAL_EDGES] (read it with ugs_batch_info)
- *   ugs_enum_fill          list[total] = the subsets as 64-bit vertex masks, graph by graph
+ *   ugs_enum_fill          list[total * ugs_enum_record_words()] = the subsets, graph by graph: one 64-bit vertex mask
+ *                          per subset, or (batches with graphs above 64 vertices) 16-byte records holding the mask or
+ *                          k 16-bit vertex ids
  *   ugs_enum_sample_batch  row = ascending vertices of list[graph][mulhi64(Philox word64, count)] (:196-210); all -1
  *                          rows for graphs without a connected k-subset (:183-191); edge_ptr = scanned per-sample column
  *                          counts; sample_ptr = g*m. Edges: ugs_eps_emit_edges (same column-scan semantics, :216-245). */
-size_t ugs_enum_scratch_bytes(int64_t G, int64_t NT);
+size_t ugs_enum_scratch_bytes(int64_t G, int64_t NT, int64_t n_general, int64_t max_n_general);
+int ugs_enum_record_words(int64_t n_general, int64_t max_n_general);
 int ugs_enum_count(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int k, int64_t n_general,
-                   void* workspace, const ugs_layout* L, void* enum_scratch, size_t enum_scratch_bytes, void* stream);
-int ugs_enum_fill(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int k, void* workspace,
-                  const ugs_layout* L, void* enum_scratch, uint64_t* list, int64_t total, void* stream);
+                   int64_t max_n_general, void* workspace, const ugs_layout* L, void* enum_scratch,
+                   size_t enum_scratch_bytes, void* stream);
+int ugs_enum_fill(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int k, int64_t n_general,
+                  int64_t max_n_general, void* workspace, const ugs_layout* L, void* enum_scratch, uint64_t* list,
+                  int64_t total, void* stream);
 int ugs_enum_sample_batch(const int64_t* ptr, int64_t G, int64_t NT, int64_t node_base, int64_t m, int k, uint64_t seed,
-                          uint64_t graph_index_base, void* workspace, const ugs_layout* L, void* enum_scratch,
-                          const uint64_t* list, void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
-                          int64_t* sample_ptr, void* stream);
+                          uint64_t graph_index_base, int64_t n_general, int64_t max_n_general, void* workspace,
+                          const ugs_layout* L, void* enum_scratch, const uint64_t* list, void* scratch,
+                          size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr, void* stream);
 
 /* ---- presample store: re-stitching cached samples into a mini-batch ---------------------------
  * Replaces Experiment._setup_presampling / _load_from_presample_cache (gps/experiment.py:379-440,895-995). The store

@@ -19,7 +19,7 @@ EXPORTS = [
     "ugs_eps_sample_batch", "ugs_eps_emit_edges", "ugs_preproc_uniform",
     "ugs_sort_scratch_bytes", "ugs_sort_columns", "ugs_apx_workspace_bytes", "ugs_apx_prepare", "ugs_apx_trials", "ugs_apx_write", "ugs_apx_dump",
     "ugs_gather_rows", "ugs_encoder_offsets", "ugs_rwr_sample_batch", "ugs_rwr_emit_edges",
-    "ugs_enum_scratch_bytes", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
+    "ugs_enum_scratch_bytes", "ugs_enum_record_words", "ugs_enum_count", "ugs_enum_fill", "ugs_enum_sample_batch",
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
     "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
@@ -98,10 +98,12 @@ def lib():
     L.ugs_rwr_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, cd, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_rwr_emit_edges.argtypes = L.ugs_emit_edges.argtypes
     L.ugs_enum_scratch_bytes.restype = sz
-    L.ugs_enum_scratch_bytes.argtypes = [i64, i64]
-    L.ugs_enum_count.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, sz, vp]
-    L.ugs_enum_fill.argtypes = [vp, i64, i64, i64, ci, vp, LP, vp, vp, i64, vp]
-    L.ugs_enum_sample_batch.argtypes = [vp, i64, i64, i64, i64, ci, u64, u64, vp, LP, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.ugs_enum_scratch_bytes.argtypes = [i64, i64, i64, i64]
+    L.ugs_enum_record_words.argtypes = [i64, i64]
+    L.ugs_enum_count.argtypes = [vp, i64, i64, i64, ci, i64, i64, vp, LP, vp, sz, vp]
+    L.ugs_enum_fill.argtypes = [vp, i64, i64, i64, ci, i64, i64, vp, LP, vp, vp, i64, vp]
+    L.ugs_enum_sample_batch.argtypes = [vp, i64, i64, i64, i64, ci, u64, u64, i64, i64, vp, LP, vp, vp, vp, sz, vp, vp,
+                                        vp, vp]
     L.ugs_presample_scratch_bytes.restype = sz
     L.ugs_presample_scratch_bytes.argtypes = [i64]
     L.ugs_presample_plan.argtypes = [vp, i64, i64, vp, i64, vp, vp, i64, vp, sz, ctypes.POINTER(i64), vp]

@@ -338,20 +338,23 @@ class DeviceBatch:
         G = max(self.G, 0)
         dev = self.device
         with torch.cuda.device(dev):
-            sb = int(L.ugs_enum_scratch_bytes(G, self.NT))
+            sb = int(L.ugs_enum_scratch_bytes(G, self.NT, self.n_general, self.max_n_general))
             es = torch.empty(sb, dtype=torch.uint8, device=dev)
-            _lib.check(L.ugs_enum_count(_ptr(self.ptr), G, self.NT, self.node_base, k, self.n_general, _ptr(self.ws),
-                                        ctypes.byref(self.layout), _ptr(es), sb, _stream()))
+            _lib.check(L.ugs_enum_count(_ptr(self.ptr), G, self.NT, self.node_base, k, self.n_general,
+                                        self.max_n_general, _ptr(self.ws), ctypes.byref(self.layout), _ptr(es), sb,
+                                        _stream()))
             total = self.info()[CTR["total_edges"]]
-            lst = torch.empty(total, dtype=torch.int64, device=dev)
-            _lib.check(L.ugs_enum_fill(_ptr(self.ptr), G, self.NT, self.node_base, k, _ptr(self.ws),
-                                       ctypes.byref(self.layout), _ptr(es), _ptr(lst), total, _stream()))
+            rw = int(L.ugs_enum_record_words(self.n_general, self.max_n_general))
+            lst = torch.empty((total, rw), dtype=torch.int64, device=dev)
+            _lib.check(L.ugs_enum_fill(_ptr(self.ptr), G, self.NT, self.node_base, k, self.n_general,
+                                       self.max_n_general, _ptr(self.ws), ctypes.byref(self.layout), _ptr(es),
+                                       _ptr(lst), total, _stream()))
         self._enum = (k, lst, es)
         return lst, es
 
     def enum_graph_offsets(self, es: torch.Tensor) -> torch.Tensor:
         G = max(self.G, 0)
-        return es[8 * self.NT: 8 * (self.NT + G + 1)].view(torch.int64)
+        return es[8 * (self.NT + 1): 8 * (self.NT + 1 + G + 1)].view(torch.int64)
 
     def sample_uniform_enum(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
                             graph_index_base: int = 0):
@@ -371,13 +374,14 @@ class DeviceBatch:
             sbytes = int(L.ugs_sample_scratch_bytes(G, m))
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
             _lib.check(L.ugs_enum_sample_batch(_ptr(self.ptr), G, self.NT, self.node_base, m, k, seed & (2 ** 64 - 1),
-                                               graph_index_base, _ptr(self.ws), ctypes.byref(self.layout), _ptr(es),
+                                               graph_index_base, self.n_general, self.max_n_general, _ptr(self.ws),
+                                               ctypes.byref(self.layout), _ptr(es),
                                                _ptr(lst), _ptr(scratch), sbytes, _ptr(nodes), _ptr(edge_ptr),
                                                _ptr(sample_ptr), _stream()))
             info = self.info()
             total = info[CTR["total_edges"]]
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
-                         n_enumerated=int(lst.numel()), n_skipped_graphs=self.n_skipped,
+                         n_enumerated=int(lst.shape[0]), n_skipped_graphs=self.n_skipped,
                          n_general_graphs=self.n_general)
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)

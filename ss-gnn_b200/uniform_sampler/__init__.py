@@ -9,8 +9,9 @@ reference it accepts tensors on any device and returns on the input device (CPU 
 
 Computed by sm_100a kernels only (csrc/ugs_enum.cu): the connected k-subsets are enumerated directly (ESU recursion
 on adjacency bitmasks), not filtered out of all C(n,k) combinations as in the reference (:47-81), so the cost follows
-the number of connected subsets. Limits: graphs with at most 64 nodes / 384 edge columns, k <= 16 (RuntimeError
-otherwise) -- the reference's exhaustive enumeration is only usable on such graphs anyway.
+the number of connected subsets. Graphs with at most 64 nodes run on 64-bit masks (k <= 16), larger ones (up to 2048
+nodes, k <= 8) on multi-word bitsets; beyond that the call raises RuntimeError -- the reference's exhaustive C(n,k)
+scan is hopeless there as well.
 Differences: Philox keyed (seed, graph, sample) instead of one mt19937_64 stream + std::uniform_int_distribution.
 """
 from __future__ import annotations

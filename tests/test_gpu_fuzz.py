@@ -69,8 +69,9 @@ def test_fuzz_uniform_enumeration(cuda_lib):
     rng0 = np.random.default_rng(404)
     for c in range(25):
         G = int(rng0.integers(1, 30))
-        ei, ptr = random_batch(rng0, G, 1, 40, deg=float(rng0.uniform(0.8, 1.8)), weird=bool(rng0.random() < 0.7))
-        k, m, mode, seed = int(rng0.integers(1, 8)), int(rng0.integers(1, 40)), MODES[int(rng0.integers(0, 3))], int(rng0.integers(0, 2 ** 40))
+        big = [(int(rng0.integers(0, G)), int(rng0.integers(65, 150)))] if rng0.random() < 0.4 else []
+        ei, ptr = random_batch(rng0, G, 1, 40, deg=float(rng0.uniform(0.8, 1.8)), weird=bool(rng0.random() < 0.7), big=big)
+        k, m, mode, seed = int(rng0.integers(1, 6 if big else 8)), int(rng0.integers(1, 40)), MODES[int(rng0.integers(0, 3))], int(rng0.integers(0, 2 ** 40))
         outs, _ = _batch(ei, ptr, k).sample_uniform_enum(m, k, mode, seed=seed)
         _eq(outs, wo.uniform_sample_batch(ei, ptr, m, k, mode, seed), ("enum", c, k, m, mode))
 

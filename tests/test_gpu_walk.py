@@ -49,7 +49,7 @@ def test_uniform_enum_bit_exact_vs_oracle(cuda_lib, mode, seed, k, m):
     # the enumerated lists themselves, graph by graph, in the oracle's order
     lst, es = b.enumerate_connected(k)
     off = b.enum_graph_offsets(es).cpu().numpy()
-    lst = lst.cpu().numpy().view(np.uint64)
+    lst = lst.cpu().numpy().view(np.uint64)[:, 0]
     for g in range(len(ptr) - 1):
         lo, n = int(ptr[g]), int(ptr[g + 1] - ptr[g])
         if n < k or n <= 0:
@@ -79,6 +79,38 @@ def test_extraction_of_reference_samples_matches_golden(cuda_lib, tag, mode):
         assert np.array_equal(eidx.cpu().numpy(), gold[f"{name}/{tag}/{mode}/edge_index_out"]), name
         assert np.array_equal(eptr.cpu().numpy(), gold[f"{name}/{tag}/{mode}/edge_ptr"]), name
         assert np.array_equal(esrc.cpu().numpy(), gold[f"{name}/{tag}/{mode}/edge_src"]), name
+
+
+@pytest.mark.parametrize("mode", ["sample", "global"])
+@pytest.mark.parametrize("seed,k,m", [(11, 3, 9), (12, 4, 5), (13, 1, 3), (14, 2, 40)])
+def test_uniform_enum_big_graphs_bit_exact_vs_oracle(cuda_lib, mode, seed, k, m):
+    """Batches mixing bitmask-path graphs, graphs with <= 64 nodes but too many columns for that path, and graphs of
+    65..200 nodes (multi-word bitsets, records of k 16-bit ids): samples bit-exact vs the oracle, lists in its order."""
+    from oracle import walk_oracle as wo
+    rng = np.random.default_rng(seed)
+    ei, ptr = random_batch(rng, 14, 1, 30, deg=1.5, weird=False, big=[(2, 130), (5, 66), (9, 200), (11, 40)])
+    # a dense small graph: 40 nodes, > 384 columns -> general path, but still 64-bit masks
+    lo, n = int(ptr[11]), int(ptr[12] - ptr[11])
+    if n >= 8:
+        extra = np.array([(lo + a, lo + b) for a in range(min(n, 30)) for b in range(a + 1, min(n, 30))], np.int64).T
+        first = int(np.searchsorted(ei[0], ptr[12]))
+        ei = np.ascontiguousarray(np.concatenate([ei[:, :first], extra, extra[::-1], ei[:, first:]], axis=1))
+    b = _batch(ei, ptr, k)
+    assert b.n_general >= 3
+    outs, stats = b.sample_uniform_enum(m, k, mode, seed=seed)
+    ref = wo.uniform_sample_batch(ei, ptr, m, k, mode, seed)
+    for a, r, nm in zip(outs, ref, ["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"]):
+        assert np.array_equal(a.cpu().numpy(), r), nm
+    lst, es = b.enumerate_connected(k)
+    off = b.enum_graph_offsets(es).cpu().numpy()
+    rec = lst.cpu().numpy()
+    assert rec.shape[1] == 2
+    for g in (2, 9):
+        lo, n = int(ptr[g]), int(ptr[g + 1] - ptr[g])
+        msk = (ei[0] >= lo) & (ei[0] < lo + n) & (ei[1] >= lo) & (ei[1] < lo + n)
+        want = wo.enumerate_connected_any(ei[:, msk] - lo, n, k)
+        ids = rec[off[g]:off[g + 1]].copy().view(np.uint16).reshape(-1, 8)[:, :k]
+        assert [tuple(int(x) for x in r) for r in ids] == want, g
 
 
 def test_laws_on_the_device(cuda_lib):
@@ -135,10 +167,13 @@ def test_dropin_modules_behave_like_the_reference(cuda_lib):
         rwr_sampler.sample_batch(tei, tptr, 5, 3, p_restart=1.5)
     with pytest.raises(RuntimeError, match="k must be >= 1"):
         rwr_sampler.sample_batch(tei, tptr, 5, 0)
-    # uniform enumeration is limited to bitmask-path graphs
+    # uniform enumeration: graphs above 64 nodes need k <= 8, above 2048 nodes are refused
     big, bptr = random_batch(np.random.default_rng(1), 2, 100, 120, deg=2.0, weird=False)
-    with pytest.raises(RuntimeError, match="<= 64 nodes"):
-        uniform_sampler.sample_batch(torch.from_numpy(big), torch.from_numpy(bptr), 2, 3)
+    with pytest.raises(RuntimeError, match="k <= 8"):
+        uniform_sampler.sample_batch(torch.from_numpy(big), torch.from_numpy(bptr), 2, 9)
+    huge = torch.stack([torch.arange(0, 2999), torch.arange(1, 3000)])
+    with pytest.raises(RuntimeError, match="<= 2048 nodes"):
+        uniform_sampler.sample_batch(huge, torch.tensor([0, 3000]), 2, 3)
 
 
 def test_qm9_shaped_completeness(cuda_lib):
