@@ -325,8 +325,9 @@ class DeviceBatch:
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
 
     def enumerate_connected(self, k: int | None = None):
-        """All connected k-subsets of every graph (uniform_sampler.cpp:47-81) as 64-bit vertex masks:
-        (list[T] int64 bit patterns, graph_off[G+1]). Cached per k; bitmask-path graphs only."""
+        """All connected k-subsets of every graph (uniform_sampler.cpp:47-81): (list[T, rw] int64, enum scratch).
+        rw = 1: one 64-bit vertex mask per subset (every graph has <= 64 vertices); rw = 2: 16-byte records holding
+        the mask (small graphs) or k 16-bit vertex ids (graphs above 64 vertices). Cached per batch."""
         L = _lib.lib()
         k = self.k if k is None else int(k)
         if k != self.k:
