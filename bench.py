@@ -411,7 +411,8 @@ def main():
                "h2d_bytes_per_step": int(h_ei.numel() * 8 + h_ptr.numel() * 8), "d2h_bytes_per_step": int(d2h),
                "host_bytes_delivered_per_step": int(delivered), "steps": args.e2e_steps,
                "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu int64 tensors; results cross PCIe packed "
-                      "(int32 / one byte per edge entry) and are widened by host threads while the copy runs"}
+                      "(16-bit deltas per 4096-value block for node ids / source columns, one byte per edge entry) and are "
+                      "widened by host threads while the copy runs"}
         del outs
 
     if rank == 0:

@@ -351,17 +351,21 @@ int ugs_wl_lookup(const uint64_t* digest, const int32_t* num_nodes, int64_t B, c
 
 /* ---- host delivery of the reference's CPU int64 ABI (reference sampler.cpp:190, ugs_sampler_batch_extension.cpp:95) -
  * The reference returns CPU pinned int64 tensors; copying them as they are is PCIe-bound (6.9 GB per ZINC-shaped call).
- * ugs_pack_outputs (device) narrows nodes and edge_src to int32 and edge_index to one byte per entry (pairs_u8 = 1: both
- * rows < 16, i.e. mode "sample" with k <= 16) or two int32 (pairs_u8 = 0) into d_wire [ugs_wire_bytes()];
+ * ugs_pack_outputs (device) narrows nodes and edge_src to int32 (delta16 = 0) or to 16-bit deltas against the minimum of
+ * their 4096-element block (delta16 = 1; ugs_pack_status tells whether every block fitted, else repack with delta16 = 0)
+ * and edge_index to one byte per entry (pairs_u8 = 1: both rows < 16, i.e. mode "sample" with k <= 16) or two int32
+ * (pairs_u8 = 0) into d_wire [ugs_wire_bytes(); the delta16 = 0 size is large enough for both];
  * ugs_fetch_outputs copies d_wire to the pinned staging buffer h_wire in chunks and widens every chunk into the final
  * int64 host arrays with n_threads host threads while the next chunks are in flight (blocks until everything has
  * arrived). Values that do not fit the packed format are counted on the device: ugs_fetch_outputs then returns
  * UGS_ELIMIT and the caller copies the int64 tensors as they are. h_edge_index is [2,total] (row 1 at +total). */
-size_t ugs_wire_bytes(int64_t B, int k, int64_t total, int pairs_u8);
+size_t ugs_wire_bytes(int64_t B, int k, int64_t total, int pairs_u8, int delta16);
 int ugs_pack_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index, const int64_t* edge_src,
-                     int64_t total, int pairs_u8, void* d_wire, void* stream);
-int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, int k, int64_t total, int pairs_u8, int64_t* h_nodes,
-                      int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, void* stream);
+                     int64_t total, int pairs_u8, int delta16, void* d_wire, void* stream);
+int ugs_pack_status(const void* d_wire, int64_t B, int k, int64_t total, int pairs_u8, int delta16, int64_t* h_bad,
+                    void* stream);
+int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, int k, int64_t total, int pairs_u8, int delta16,
+                      int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, void* stream);
 
 /* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
  * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in

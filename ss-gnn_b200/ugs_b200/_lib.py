@@ -23,7 +23,7 @@ EXPORTS = [
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
     "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
-    "ugs_wire_bytes", "ugs_pack_outputs", "ugs_fetch_outputs", "ugs_emit_edges_packed", "ugs_sample_batch_early",
+    "ugs_wire_bytes", "ugs_pack_outputs", "ugs_pack_status", "ugs_fetch_outputs", "ugs_emit_edges_packed", "ugs_sample_batch_early",
 ]
 
 
@@ -118,9 +118,10 @@ def lib():
     L.ugs_emit_edges_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp, sz, vp]
     L.ugs_sample_batch_early.argtypes = [vp, i64, i64, i64, ci, u64, u64, u64, ci, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp, vp]
     L.ugs_wire_bytes.restype = sz
-    L.ugs_wire_bytes.argtypes = [i64, ci, i64, ci]
-    L.ugs_pack_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, vp, vp]
-    L.ugs_fetch_outputs.argtypes = [vp, vp, i64, ci, i64, ci, vp, vp, vp, ci, vp]
+    L.ugs_wire_bytes.argtypes = [i64, ci, i64, ci, ci]
+    L.ugs_pack_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, ci, vp, vp]
+    L.ugs_pack_status.argtypes = [vp, i64, ci, i64, ci, ci, ctypes.POINTER(i64), vp]
+    L.ugs_fetch_outputs.argtypes = [vp, vp, i64, ci, i64, ci, ci, vp, vp, vp, ci, vp]
     _LIB = L
     return L
 

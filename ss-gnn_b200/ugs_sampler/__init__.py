@@ -97,7 +97,7 @@ def _to_host_batch(outs, mode: str, k: int):
     pairs = 1 if (mode == "sample" and int(k) <= 16) else 0
     dev = nodes.device
     with torch.cuda.device(dev):
-        wb = int(L.ugs_wire_bytes(B, kk, total, pairs))
+        wb = int(L.ugs_wire_bytes(B, kk, total, pairs, 0))  # the int32 layout is large enough for both formats
         d_wire = torch.empty(wb, dtype=torch.uint8, device=dev)
         h_wire = torch.empty(wb, dtype=torch.uint8, pin_memory=True)
         h_nodes = torch.empty(nodes.shape, dtype=torch.int64, pin_memory=True)
@@ -105,17 +105,26 @@ def _to_host_batch(outs, mode: str, k: int):
         h_esrc = torch.empty(esrc.shape, dtype=torch.int64, pin_memory=True)
         h_eptr = torch.empty(eptr.shape, dtype=torch.int64, pin_memory=True)
         h_sptr = torch.empty(sptr.shape, dtype=torch.int64, pin_memory=True)
-        _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx.contiguous()), _ptr(esrc), total, pairs,
+        eidx_c = eidx.contiguous()
+        # node ids / source columns as 16-bit deltas per 4096-element block; int32 if some block spreads too far
+        delta16 = 1
+        _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx_c), _ptr(esrc), total, pairs, delta16,
                                       _ptr(d_wire), _stream()))
+        bad = ctypes.c_int64(0)
+        _lib.check(L.ugs_pack_status(_ptr(d_wire), B, kk, total, pairs, delta16, ctypes.byref(bad), _stream()))
+        if bad.value:
+            delta16 = 0
+            _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx_c), _ptr(esrc), total, pairs, delta16,
+                                          _ptr(d_wire), _stream()))
         h_eptr.copy_(eptr, non_blocking=True)
         h_sptr.copy_(sptr, non_blocking=True)
-        rc = L.ugs_fetch_outputs(_ptr(d_wire), ctypes.c_void_p(h_wire.data_ptr()), B, kk, total, pairs,
+        rc = L.ugs_fetch_outputs(_ptr(d_wire), ctypes.c_void_p(h_wire.data_ptr()), B, kk, total, pairs, delta16,
                                  ctypes.c_void_p(h_nodes.data_ptr()), ctypes.c_void_p(h_eidx.data_ptr()),
                                  ctypes.c_void_p(h_esrc.data_ptr()), _host_threads(), _stream())
         torch.cuda.current_stream().synchronize()
         if rc != 0:  # a value outside the packed ranges (never for valid sampler output): plain copy
             return _to_host(outs)
-    _to_host_batch.last_d2h_bytes = wb + 8 * (eptr.numel() + sptr.numel())
+    _to_host_batch.last_d2h_bytes = int(L.ugs_wire_bytes(B, kk, total, pairs, delta16)) + 8 * (eptr.numel() + sptr.numel())
     return [h_nodes, h_eidx, h_eptr, h_sptr, h_esrc]
 
 

@@ -184,6 +184,16 @@ def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
         for a, b in zip(packed, plain):
             assert a.dtype == torch.int64 and a.is_pinned() and not a.is_cuda
             assert torch.equal(a, b)
+    # one graph with 120k columns: source columns of neighbouring entries are far apart -> the 16-bit frame-of-reference
+    # packing overflows and the int32 wire format takes over
+    from ugs_b200 import synth as _synth
+    bei, bptr = _synth.barabasi_albert(20000, 3, 7)
+    a = ugs_sampler.sample_batch(torch.from_numpy(bei), torch.from_numpy(bptr), 3000, 5, mode, 2)
+    assert ugs_sampler._to_host_batch.last_d2h_bytes > 4 * a[4].numel()  # int32 source columns, not 16-bit deltas
+    monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+    b = ugs_sampler.sample_batch(torch.from_numpy(bei), torch.from_numpy(bptr), 3000, 5, mode, 2)
+    monkeypatch.delenv("UGS_B200_PACKED_D2H")
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
     # odd sizes / a single host thread / k > 16 (two int32 per entry) / empty edge list
     monkeypatch.setenv("UGS_B200_HOST_THREADS", "1")
     ei2, ptr2 = random_batch(np.random.default_rng(9), 23, 1, 60, deg=2.5, big=[(3, 200)])
