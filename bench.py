@@ -192,6 +192,14 @@ def cpu_reference_throughput(ei, ptr, m, k, seed, n_graphs, procs, chunk=256):
                       f"same graphs with every preprocessing cached ({wall_warm:.2f}s)"}
 
 
+def workload_name(workload: str, graphs_per_rank: int) -> str:
+    """The `config.workload` string, shared by both arms."""
+    if workload == "zinc":
+        return (f"zinc-shaped batch (BASELINE configs[3]: 1M graphs k=8 m=64 sharded by graph over 8 GPUs -> "
+                f"{graphs_per_rank} graphs per rank)")
+    return f"{workload}-shaped batch"
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -211,7 +219,9 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_sample * m / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shaped, k={k}, m={m}", "graphs_per_step": n_sample},
+        "config": {"workload": workload_name(args.workload, G), "k": k, "m": m, "graphs_per_rank": G,
+                   "graphs_per_step": n_sample,
+                   "sample": f"each step = the first {n_sample} graphs of that workload on all host cores"},
         "cpu_baseline": dict(last, value=v),
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -432,9 +442,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if sample_sharded else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}-shaped batch (BASELINE configs[3]: 1M graphs k=8 m=64 sharded by graph "
-                            f"over 8 GPUs -> {G} graphs per rank)" if args.workload == "zinc"
-                            else f"{args.workload}-shaped batch",
+                "workload": workload_name(args.workload, G),
                 "k": k, "m": m, "graphs_per_rank": G, "nodes_per_rank": NT, "edge_columns_per_rank": E,
                 "mean_edge_entries_per_graphlet": ebar, "l2": "512 MiB flush between timed iterations",
                 "sharding": (f"dp{world} by sample of one replicated graph (m={m_job} split), no data-path collective"
