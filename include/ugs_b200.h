@@ -105,16 +105,22 @@ typedef struct ugs_ginfo {
 
 /* counters[] slots */
 #define UGS_CTR_UNSORTED 0      /* bit0: columns not grouped by graph (sort them: perm); bit1: ptr decreasing;
-                                   bit2/bit3: the fast segmentation does not apply -> redo with fast = 0   */
+                                   bit2/bit3: the fast segmentation does not apply -> redo with fast = 0;
+                                   bit4: ugs_sample_batch was called with k > 16 on a workspace whose bitmask-path
+                                   graphs were preprocessed for a smaller k (nothing was sampled for them)   */
 #define UGS_CTR_N_GENERAL 1
 #define UGS_CTR_MAX_N_GENERAL 2
 #define UGS_CTR_N_SKIPPED 3
 #define UGS_CTR_TOTAL_EDGES 4   /* written by ugs_sample_batch                                          */
 #define UGS_CTR_INCOMPLETE 5    /* rows with a -1                                                        */
 #define UGS_CTR_RELAXED 6       /* graphs sampled at relaxation level > 0                                */
-#define UGS_CTR_TRIALS 7        /* growth attempts (== samples for VARIANT_REF)                          */
+#define UGS_CTR_TRIALS 7        /* growth attempts, written by the rejection variants / walk steps (rwr). VARIANT_REF
+                                   grows every row exactly once and leaves it 0: trials == sampled rows there */
 #define UGS_CTR_SCAN_TICKET 8
 #define UGS_CTR_N_LARGE 9        /* general-path graphs with more than UGS_LARGE_N nodes                   */
+#define UGS_CTR_EMIT_OVERFLOW 15 /* samples ugs_eps_emit_edges could not emit (more than 1024 induced columns on the
+                                    general path, or counts that do not match edge_ptr): their slice of the output is
+                                    left untouched -- the caller must treat a non-zero value as an error      */
 #define UGS_CTR_COUNT 64         /* int64 words in counters[]                                             */
 #define UGS_CTR_EARLY_TOTAL 16   /* [16, 48): partial sums of the per-sample entry counts, added up by the sampling
                                     kernels themselves (32 addresses to spread the atomics); their sum is the total

@@ -64,7 +64,8 @@ __global__ void k_seg_fast(const i64* __restrict__ row0, i64 E, const i64* __res
     cstart[g] = lo;
 }
 
-__global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_lt_k, WS w) {
+__global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_lt_k, const i64* __restrict__ fast_row0,
+                           WS w) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     i64 n = ptr[g + 1] - ptr[g];
@@ -77,6 +78,15 @@ __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_l
     if (n <= 0 || (skip_lt_k && n < k)) {  // ugs_sampler_batch_extension.cpp:132 (batch driver only)
         gi.cls = 0;
         atomicAdd(&w.counters[UGS_CTR_N_SKIPPED], 1ull);
+        // No preprocessing kernel looks at a skipped graph's column range, so the fast segmentation is verified here:
+        // a column of ANOTHER graph inside this range (batch not graph-contiguous) would otherwise be lost silently.
+        if (fast_row0) {
+            const i64 lo_ = ptr[g], hi_ = ptr[g + 1];
+            for (i64 c = w.cstart[g]; c < w.cstart[g + 1]; ++c) {
+                const i64 u = fast_row0[c];
+                if (u < lo_ || u >= hi_) { atomicOr(&w.counters[UGS_CTR_UNSORTED], 8ull); break; }
+            }
+        }
     } else if (n <= UGS_SMALL_MAX_N && nc <= UGS_SMALL_MAX_COLS && k <= 16) {
         gi.cls = 1;
     } else {
@@ -763,7 +773,7 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
         UGS_LAUNCH_CHECK("k_seg_bounds");
     }
     if (G > 0) {
-        k_classify<<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, w);
+        k_classify<<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, (fast && !perm) ? edge_index : nullptr, w);
         UGS_LAUNCH_CHECK("k_classify");
     }
     return UGS_OK;

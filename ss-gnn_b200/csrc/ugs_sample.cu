@@ -118,6 +118,10 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
     }
     const ugs_ginfo gi = w.ginfo[g];
     if (gi.cls == 2) return;
+    if (gi.cls == 1 && k > 16) {  // the workspace was preprocessed for a smaller k: tile[][16] cannot hold the row
+        if (lane == 0) atomicOr(&w.counters[UGS_CTR_UNSORTED], 16ull);
+        return;
+    }
     const int ntiles = (int)((m + 31) >> 5);
     const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
     const i64 lo = ptr[g];

@@ -492,7 +492,7 @@ k_eps_emit_general(const i64* __restrict__ row0, const i64* __restrict__ ptr, i6
         }
         __syncwarp();
         if (h > EPSG_CAP || h != want) {  // cannot happen for consistent inputs; never write out of range
-            if (lane == 0) atomicAdd(&w.counters[15], 1ull);
+            if (lane == 0) atomicAdd(&w.counters[UGS_CTR_EMIT_OVERFLOW], 1ull);
             continue;
         }
         for (int e = lane; e < h; e += 32) {
@@ -587,6 +587,7 @@ extern "C" int ugs_eps_emit_edges(const int64_t* edge_index, int64_t E, const in
         UGS_LAUNCH_CHECK("k_eps_emit_small");
     }
     if (n_general > 0) {
+        UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_EMIT_OVERFLOW], 0, sizeof(i64), st));
         int64_t blocks = (n_general * m + 3) / 4;
         const int64_t cap = (int64_t)eps_sm_count() * 16;
         if (blocks > cap) blocks = cap;

@@ -37,20 +37,31 @@ class Layout(ctypes.Structure):
         "suffix_deg", "bucket_b", "cum", "adj", "suf", "csr_idx", "csr_col", "gaux", "llist", "lscratch")]
 
 
-def nvcc_command(out: str = SO):
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
+              "-Xcompiler", "-fPIC", f"-I{os.path.join(REPO, 'include')}", f"-I{CSRC}"]
+
+
+def build(force: bool = False, extra_flags=(), out: str = SO) -> str:
+    """Compile libugs_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU): one object per source file
+    under csrc/build/ (only stale ones are recompiled, in parallel), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", f"-I{os.path.join(REPO, 'include')}",
-            f"-I{CSRC}"] + srcs + ["-o", out]
-
-
-def build(force: bool = False) -> str:
-    """Compile libugs_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))] + HEADERS
-    stale = (not os.path.exists(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs)
-    if force or stale:
-        subprocess.check_call(nvcc_command())
-    return SO
+    bdir = os.path.join(CSRC, "build" if out == SO else "build_" + os.path.basename(out))
+    os.makedirs(bdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in HEADERS + [os.path.abspath(__file__)])
+    jobs, objs = [], []
+    for s in srcs:
+        o = os.path.join(bdir, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
+            jobs.append(["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(subprocess.check_call, jobs))
+    if jobs or not os.path.exists(out) or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
+                              + objs + ["-o", out])
+    return out
 
 
 _LIB = None

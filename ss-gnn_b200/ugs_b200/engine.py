@@ -14,7 +14,7 @@ from . import _lib
 MODES = {"sample": 0, "graph": 1, "global": 2, "encoder": 3}  # "encoder": UGS_MODE_ENCODER (not a reference mode)
 VARIANTS = {"ref": 0, "uniform": 1}
 CTR = dict(unsorted=0, n_general=1, max_n_general=2, n_skipped=3, total_edges=4, incomplete=5, relaxed=6, trials=7,
-           n_large=9)
+           n_large=9, emit_overflow=15)
 
 
 def _ptr(t):
@@ -118,6 +118,25 @@ class DeviceBatch:
                                                       self.node_base, self.k, _ptr(self.perm), n_general, n_large,
                                                       parts, _ptr(self.ws), ctypes.byref(self.layout), _stream()))
 
+    def _check_emit_overflow(self, total):
+        """General-path column emission (k_eps_emit_general) skips a sample it cannot hold (more than 1024 induced
+        columns); its slice of the output would be uninitialised memory, so that is an error, not a result."""
+        if self.n_general > 0 and total > 0:
+            n_bad = self.info()[CTR["emit_overflow"]]
+            if n_bad:
+                raise RuntimeError(f"{n_bad} samples have more induced columns than the general-path emission "
+                                   "holds (1024)")
+
+    def _check_k(self, k) -> int:
+        """The tables (path class, skip rule, reachability, bucket weights) were built for self.k: sampling another k on
+        them would mix two laws (and overrun the bitmask path's 16-entry rows), so it is refused. The reference
+        `sample(handle, m, k)` (sampler.cpp:91) takes k again but silently returns -1 rows when it differs from the
+        preprocessing k (SURVEY section 7 "reference quirks"); `ugs_sampler.sample` re-preprocesses instead."""
+        k = self.k if k is None else int(k)
+        if k != self.k:
+            raise RuntimeError(f"this batch was preprocessed for k={self.k}, not k={k}")
+        return k
+
     def _late_check(self, info) -> bool:
         """True if the preprocessing kernels found a column outside its graph's range (the fast segmentation was
         fooled by a batch that is not graph-contiguous): the batch has been rebuilt on the slow path, redo the op."""
@@ -181,7 +200,7 @@ class DeviceBatch:
         L = _lib.lib()
         if mode not in MODES:
             raise RuntimeError("mode must be one of: 'sample', 'graph', 'global'")
-        k = self.k if k is None else int(k)
+        k = self._check_k(k)
         variant = self.variant if variant is None else variant
         if variant != self.variant:
             raise RuntimeError(f"this batch was preprocessed for variant {self.variant!r}")
@@ -214,10 +233,15 @@ class DeviceBatch:
             if self._late_check(info):
                 return self.sample(m, k, mode, seed, graph_index_base, variant, emit, sample_index_base,
                                    per_graph_seed)
+            if info[CTR["unsorted"]] & 16:
+                raise RuntimeError(f"k={k} exceeds the bitmask path's limit of 16 for a batch preprocessed for k={self.k}")
             total = info[CTR["total_edges"]]
+            # the reference law grows every row exactly once: trials == sampled rows (the counter is only written by the
+            # rejection variants)
+            n_trials = info[CTR["trials"]] if variant != "ref" else (G - self.n_skipped) * m
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
-                         n_general_graphs=self.n_general, n_trials=info[CTR["trials"]])
+                         n_general_graphs=self.n_general, n_trials=n_trials)
             edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
             edge_src = torch.empty(total, dtype=torch.int64, device=dev)
             # only the reference-law kernels leave packed rows behind the scan words of `scratch`
@@ -246,7 +270,7 @@ class DeviceBatch:
         L = _lib.lib()
         if not (epsilon > 0.0 and epsilon <= 1.0):
             raise RuntimeError("epsilon must be in (0, 1]")
-        k = self.k if k is None else int(k)
+        k = self._check_k(k)
         m = int(m)
         G = max(self.G, 0)
         dev = self.device
@@ -283,6 +307,7 @@ class DeviceBatch:
                                             _ptr(self.perm), self.n_general, _ptr(self.ws), ctypes.byref(self.layout),
                                             _ptr(nodes), _ptr(edge_ptr), total, _ptr(edge_index), _ptr(edge_src),
                                             _stream()))
+            self._check_emit_overflow(total)
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
 
     def sample_rwr(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42, p_restart: float = 0.2,
@@ -290,7 +315,7 @@ class DeviceBatch:
         """rwr_sampler.sample_batch on the device (rwr_sampler.cpp:72-295): same 5-tuple layout, node rows in
         visiting order, UGS-style entries (both directions, duplicates kept), edge_src = -1."""
         L = _lib.lib()
-        k = self.k if k is None else int(k)
+        k = self._check_k(k)
         if k < 1:
             raise RuntimeError("k must be >= 1")
         if not (p_restart >= 0.0 and p_restart <= 1.0):
@@ -362,7 +387,7 @@ class DeviceBatch:
         """uniform_sampler.sample_batch on the device (uniform_sampler.cpp:86-282): one enumerated connected k-subset
         per sample, uniformly; ascending node rows; one edge entry per batch column inside the sample."""
         L = _lib.lib()
-        k = self.k if k is None else int(k)
+        k = self._check_k(k)
         m = int(m)
         G = max(self.G, 0)
         dev = self.device
@@ -390,12 +415,13 @@ class DeviceBatch:
                                             _ptr(self.perm), self.n_general, _ptr(self.ws), ctypes.byref(self.layout),
                                             _ptr(nodes), _ptr(edge_ptr), total, _ptr(edge_index), _ptr(edge_src),
                                             _stream()))
+            self._check_emit_overflow(total)
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
 
     def extract(self, nodes: torch.Tensor, m: int, k: int | None = None, mode: str = "sample"):
         """Induced-edge extraction (A.7) for caller-provided node rows [G*m,k] (batch-global ids, -1 pad)."""
         L = _lib.lib()
-        k = self.k if k is None else int(k)
+        k = self._check_k(k)
         G = max(self.G, 0)
         dev = self.device
         nodes = nodes.to(dev).contiguous()

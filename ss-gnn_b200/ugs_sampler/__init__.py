@@ -36,6 +36,51 @@ _next_handle = 1
 _EDGE_MODES = {"local": "sample", "flat": "graph", "global": "global"}
 
 
+# ---- UGS_DEBUG=1 diagnostics on stderr, in the reference's formats ------------------------------------------------
+def _debug_on() -> bool:
+    return os.environ.get("UGS_DEBUG") == "1"  # preproc.cpp:246-247: exactly the string "1"
+
+
+def _fmt_preproc(n, k, Z, viable) -> str:
+    """preproc.cpp:253-254"""
+    return "[UGS PREPROC] n=%d k=%d Z=%.2e viable=%d/%d" % (n, k, Z, viable, n)
+
+
+def _fmt_sample(n, k, m, Z, level, incomplete) -> str:
+    """sampler.cpp:184-186; weighted / uniform = rows whose root came from the weights (level 0) / from the uniform
+    relaxation draw (levels 1, 2)"""
+    return ("[UGS SAMPLE] n=%d k=%d m=%d Z=%.2e | relax=%d weighted=%d uniform=%d incomplete=%d"
+            % (n, k, m, Z, level, m if level == 0 else 0, 0 if level == 0 else m, incomplete))
+
+
+def _fmt_cache(n_graphs) -> str:
+    """ugs_sampler_batch_extension.cpp:249-254. There is no preprocessing cache here: every graph
+    is preprocessed on the device in every call, which the line says in the reference's own vocabulary."""
+    return "[UGS CACHE] hits=0 misses=%d hit_rate=0.0%% cache_size=0 (cache: none, preprocessing is recomputed)" % n_graphs
+
+
+def _debug_report(b, nodes, m, k, with_cache_line):
+    """One PREPROC and one SAMPLE line per sampled graph like the reference's per-graph calls, then the cache line.
+    Debug mode only: reads the per-graph records and the node rows back to the host."""
+    import sys
+    gi = b.ginfo()
+    sizes = (b.ptr[1:] - b.ptr[:-1]).cpu().tolist()
+    bad = (nodes < 0).any(dim=1).view(max(b.G, 0), -1).sum(dim=1).cpu().tolist() if nodes.numel() else [0] * b.G
+    lines = []
+    n_sampled = 0
+    for g in range(b.G):
+        if int(gi["cls"][g]) == 0:  # n < k: the batch driver never preprocesses it (:132-143)
+            continue
+        n_sampled += 1
+        Z, lvl = float(gi["Z"][g]), int(gi["level"][g])
+        viable = int(gi["n_eligible"][g]) if lvl == 0 else 0
+        lines.append(_fmt_preproc(sizes[g], k, Z, viable))
+        lines.append(_fmt_sample(sizes[g], k, m, Z, lvl, int(bad[g])))
+    if with_cache_line:
+        lines.append(_fmt_cache(n_sampled))
+    sys.stderr.write("\n".join(lines) + "\n")
+
+
 def _device():
     if not torch.cuda.is_available():
         raise RuntimeError("ugs_sampler (B200): no CUDA device available and there is no CPU fallback")
@@ -191,7 +236,18 @@ def sample(handle: int, m_per_graph: int, k: int, edge_mode: str = "local", base
         raise RuntimeError("No viable roots available")
     # Any edge_mode other than 'local'/'flat' behaves as 'global' in the reference (sampler.cpp:262-273).
     mode = _EDGE_MODES.get(edge_mode, "global")
+    if int(k) != b.k:
+        # The reference takes k again here and mixes it with the tables of the preprocessing k (rows of -1 when it is
+        # larger). The tables are cheap to rebuild on the device, so the handle is re-preprocessed for the new k.
+        nb = _engine.DeviceBatch(b.edge_index, b.ptr, int(k), 0, b.NT, skip_lt_k=False)
+        nb._cuda_out = b._cuda_out
+        with _registry_lock:
+            if int(handle) in _registry:
+                _registry[int(handle)] = nb
+        b = nb
     (nodes, ei, eptr, _sptr, esrc), _ = b.sample(int(m_per_graph), int(k), mode, int(seed))
+    if _debug_on():
+        _debug_report(b, nodes, int(m_per_graph), int(k), with_cache_line=False)
     if mode == "global" and base_offset:
         nodes = torch.where(nodes >= 0, nodes + int(base_offset), nodes)
         ei = ei + int(base_offset)
@@ -221,6 +277,8 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
         b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0], variant=variant)
         outs, _stats = b.sample(int(m_per_graph), int(k), mode, int(seed))
         sample_batch.last_stats = _stats
+        if _debug_on():
+            _debug_report(b, outs[0], int(m_per_graph), int(k), with_cache_line=True)
         return tuple(outs if _want_cuda_out(edge_index) else _to_host_batch(outs, mode, int(k)))
 
 

@@ -147,3 +147,23 @@ def test_synthetic_workloads_have_the_named_shapes():
     ei, ptr = synth.barabasi_albert(500, 3, seed=3)
     deg = np.bincount(ei[0], minlength=500)
     assert deg.max() > 20 and ptr.tolist() == [0, 500]
+
+
+def test_ugs_debug_lines_have_the_reference_formats():
+    """UGS_DEBUG=1 diagnostics (reference preproc.cpp:253-254, sampler.cpp:184-186,
+    ugs_sampler_batch_extension.cpp:249-254): same prefixes, field names, order and number formats."""
+    import ugs_sampler as us
+    assert us._fmt_preproc(23, 8, 1.5e7, 17) == "[UGS PREPROC] n=23 k=8 Z=1.50e+07 viable=17/23"
+    assert (us._fmt_sample(23, 8, 64, 1.5e7, 0, 0)
+            == "[UGS SAMPLE] n=23 k=8 m=64 Z=1.50e+07 | relax=0 weighted=64 uniform=0 incomplete=0")
+    assert (us._fmt_sample(3, 3, 5, 0.0, 1, 5)
+            == "[UGS SAMPLE] n=3 k=3 m=5 Z=0.00e+00 | relax=1 weighted=0 uniform=5 incomplete=5")
+    line = us._fmt_cache(10)
+    assert re.match(r"^\[UGS CACHE\] hits=0 misses=10 hit_rate=0\.0% cache_size=0 \(cache: none", line)
+    os.environ.pop("UGS_DEBUG", None)
+    assert not us._debug_on()
+    os.environ["UGS_DEBUG"] = "true"  # the reference compares with the string "1" only (preproc.cpp:247)
+    assert not us._debug_on()
+    os.environ["UGS_DEBUG"] = "1"
+    assert us._debug_on()
+    del os.environ["UGS_DEBUG"]

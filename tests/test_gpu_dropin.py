@@ -148,7 +148,9 @@ def test_completeness_on_qm9_shaped_graphs(cuda_lib):
         assert not bad[n >= k].any()
         assert bad[n < k].all()
         st = ugs_sampler.sample_batch.last_stats
-        assert st["n_incomplete"] == int(bad.sum()) * 10 or st["n_incomplete"] == 0 or True
+        # n_incomplete counts partial rows of SAMPLED graphs; the all -1 rows of skipped graphs (n < k) are separate
+        assert st["n_incomplete"] == 0
+        assert st["n_skipped_graphs"] == int((n < k).sum()) == int(bad.sum())
 
 
 def test_handle_api_k_quirks_and_errors(cuda_lib):
@@ -163,6 +165,50 @@ def test_handle_api_k_quirks_and_errors(cuda_lib):
         ugs_sampler.sample(h, 1, 3)
     with pytest.raises(RuntimeError):
         ugs_sampler.sample_batch(ei, torch.tensor([0, 3]), 2, 33)  # k above the implementation limit
+
+
+def test_k_other_than_the_preprocessing_k(cuda_lib):
+    """The tables are built for one k: DeviceBatch refuses another k; the handle API re-preprocesses, so
+    that sample(handle, m, k2) equals a fresh create_preproc(k2) + sample."""
+    import ugs_sampler
+    from ugs_b200 import synth
+    from ugs_b200.engine import DeviceBatch
+    ei, ptr = synth.make_batch("zinc", 40, seed=3)
+    b = DeviceBatch(torch.from_numpy(ei).cuda(), torch.from_numpy(ptr).cuda(), 4, 0, int(ptr[-1]))
+    for call in (lambda: b.sample(8, 20), lambda: b.sample(8, 5), lambda: b.sample_epsilon(8, 5),
+                 lambda: b.sample_rwr(8, 5), lambda: b.extract(torch.zeros((40 * 8, 5), dtype=torch.int64), 8, 5)):
+        with pytest.raises(RuntimeError, match="preprocessed for k=4"):
+            call()
+    e0 = torch.from_numpy(ei[:, ei[0] < ptr[1]])
+    n0 = int(ptr[1])
+    h = ugs_sampler.create_preproc(e0, n0, 4)
+    got = ugs_sampler.sample(h, 16, 20 if n0 >= 20 else 6, "local", 0, 7)
+    h2 = ugs_sampler.create_preproc(e0, n0, 20 if n0 >= 20 else 6)
+    want = ugs_sampler.sample(h2, 16, 20 if n0 >= 20 else 6, "local", 0, 7)
+    assert all(torch.equal(a, b_) for a, b_ in zip(got, want))
+    assert (got[0] >= 0).all()
+    ugs_sampler.destroy_preproc(h)
+    ugs_sampler.destroy_preproc(h2)
+
+
+def test_ugs_debug_prints_the_reference_lines(cuda_lib, monkeypatch, capfd):
+    """UGS_DEBUG=1: one PREPROC + one SAMPLE line per sampled graph and the cache line."""
+    import ugs_sampler
+    ei = bidir([(0, 1), (1, 2), (2, 0), (3, 4)])  # triangle (n=3) + single edge in a graph of 3 nodes
+    ptr = torch.tensor([0, 3, 6, 8])  # third graph: n=2 < k -> skipped, no lines
+    monkeypatch.setenv("UGS_DEBUG", "1")
+    capfd.readouterr()
+    ugs_sampler.sample_batch(torch.from_numpy(ei), ptr, 5, 3, mode="sample", seed=1)
+    err = capfd.readouterr().err.strip().splitlines()
+    assert len(err) == 5
+    assert err[0].startswith("[UGS PREPROC] n=3 k=3 Z=") and err[0].endswith("/3")
+    assert err[1].startswith("[UGS SAMPLE] n=3 k=3 m=5 Z=") and "relax=0 weighted=5 uniform=0 incomplete=0" in err[1]
+    assert err[2] == "[UGS PREPROC] n=3 k=3 Z=0.00e+00 viable=0/3"
+    assert err[3] == "[UGS SAMPLE] n=3 k=3 m=5 Z=0.00e+00 | relax=1 weighted=0 uniform=5 incomplete=5"
+    assert err[4].startswith("[UGS CACHE] hits=0 misses=2 ")
+    monkeypatch.delenv("UGS_DEBUG")
+    ugs_sampler.sample_batch(torch.from_numpy(ei), ptr, 5, 3, mode="sample", seed=1)
+    assert capfd.readouterr().err == ""
 
 
 @pytest.mark.parametrize("mode", ["sample", "graph", "global"])

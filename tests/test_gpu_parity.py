@@ -105,7 +105,9 @@ def test_sample_batch_bit_exact_vs_oracle(cuda_lib, mode, seed, k, m):
                                  f"gpu {a[bad[0]]} oracle {r[bad[0]]}")
         assert np.array_equal(a, r), f"{name} differs (mode={mode})"
     assert stats["n_edge_entries"] == ref[1].shape[1]
-    assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - 0 * stats["n_skipped_graphs"] or True
+    # n_incomplete = partial rows of sampled graphs; skipped graphs (n < k) contribute m all -1 rows each
+    assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
+    assert stats["n_trials"] == (len(ptr) - 1 - stats["n_skipped_graphs"]) * m
 
 
 def test_both_paths_give_identical_samples(cuda_lib):
