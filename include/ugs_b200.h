@@ -118,6 +118,7 @@ typedef struct ugs_ginfo {
                                    grows every row exactly once and leaves it 0: trials == sampled rows there */
 #define UGS_CTR_SCAN_TICKET 8
 #define UGS_CTR_N_LARGE 9        /* general-path graphs with more than UGS_LARGE_N nodes                   */
+#define UGS_CTR_WORK 14          /* work-claim cursor of the persistent general-path sampling kernel          */
 #define UGS_CTR_EMIT_OVERFLOW 15 /* samples ugs_eps_emit_edges could not emit (more than 1024 induced columns on the
                                     general path, or counts that do not match edge_ptr): their slice of the output is
                                     left untouched -- the caller must treat a non-zero value as an error      */

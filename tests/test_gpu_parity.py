@@ -277,3 +277,39 @@ def test_column_sort_is_stable_on_many_graphs(cuda_lib):
     ref = _oracle_batch(ei2, ptr, 4, 3, "sample", 6)
     for a, r in zip(outs, ref):
         assert np.array_equal(a.cpu().numpy(), r)
+
+
+@pytest.mark.parametrize("n,k,m", [(100000, 6, 1000), (30000, 6, 3000), (100000, 3, 500)])
+def test_powerlaw_graph_at_baseline_size_bit_exact(cuda_lib, n, k, m):
+    """BASELINE configs[4] at its full size: ONE Barabasi-Albert graph with 10^5 nodes (hub rows of thousands of
+    entries, L2-resident CSR, two-level cut bitmap of the general-path sampler, cooperative preprocessing kernel):
+    every table and all five outputs bit-exact against the oracle."""
+    from ugs_b200 import synth
+    ei, ptr = synth.barabasi_albert(n, 3, seed=7)
+    b = _batch(ei, ptr, k)
+    assert b.n_large == 1 and b.n_general == 1
+    _check_tables(b, ei, ptr, k)
+    outs, stats = b.sample(m, k, "sample", seed=4)
+    ref = _oracle_batch(ei, ptr, m, k, "sample", 4)
+    for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+        assert np.array_equal(a.cpu().numpy(), r), name
+    assert stats["n_incomplete"] == 0 and stats["n_edge_entries"] == ref[1].shape[1]
+    # the same rows when the samples are split over two "ranks" (SURVEY 8e: one huge graph is sharded by sample)
+    half = m // 2
+    lo_, _ = b.sample(half, k, "sample", seed=4)
+    hi_, _ = b.sample(m - half, k, "sample", seed=4, sample_index_base=half)
+    assert np.array_equal(torch.cat([lo_[0], hi_[0]]).cpu().numpy(), ref[0])
+
+
+def test_general_path_sampler_block_boundaries(cuda_lib):
+    """General-path graphs whose sizes straddle the two-level cut bitmap's block size (1024 vertices = 32 words) and
+    multi-pass block scans (> 32 blocks), dense enough that the cut spans many blocks."""
+    rng = np.random.default_rng(77)
+    sizes = [65, 1023, 1024, 1025, 2048, 3000, 33 * 1024 + 5]
+    ei, ptr = random_batch(rng, len(sizes), 5, 30, deg=6.0, weird=False, big=list(enumerate(sizes)))
+    for k in (4, 9):
+        b = _batch(ei, ptr, k)
+        outs, _ = b.sample(200, k, "global", seed=11)
+        ref = _oracle_batch(ei, ptr, 200, k, "global", 11)
+        for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r), (name, k)
