@@ -99,7 +99,8 @@ typedef struct ugs_ginfo {
     int32_t level;       /* relaxation level 0/1/2 (sampler.cpp:125-146); -1 if the graph is skipped */
     int32_t n_eligible;  /* #root positions eligible at that level; level 0 = bucket_count_nonzero   */
     int32_t last_viable; /* largest position with bucket_b > 0 (root-draw guard)                     */
-    int32_t mult;        /* >0: every adjacent pair appears exactly `mult` times per row, no self loops */
+    int32_t mult;        /* bitmask path: >0 = every adjacent pair appears exactly `mult` times per row and there are
+                            no self loops, 0 = irregular; general path: -1 = no self-loop column, 0 = some */
     int32_t cls;         /* 0 = skipped (n <= 0 or n < k), 1 = bitmask path, 2 = general path        */
 } ugs_ginfo;
 
@@ -229,6 +230,25 @@ int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node_base, int6
 int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
                     void* workspace, const ugs_layout* L, void* scratch, size_t scratch_bytes,
                     const int64_t* nodes, int64_t* edge_ptr, void* stream);
+
+/* ---- small batches: the whole pipeline in one call with one host round trip (csrc/ugs_fused.cu) -----------------
+ * What ugs_sampler.sample_batch costs for a DataLoader mini-batch (gps/experiment.py:882-883) is launch latency and
+ * host round trips, not kernel time. ugs_sample_batch_fused queues segment -> preprocess -> sample -> scan -> emit
+ * back to back (UGS_VARIANT_REF, graph-contiguous columns): the general-path kernels get worst-case grids and read
+ * their item counts from counters[] on the device, and the emission pass writes into ei_u / ei_v (= ei_u + cap) /
+ * ei_src of cap >= ugs_fused_capacity(E, m) = 2*E*m entries (a sample emits every CSR entry at most once). The stream
+ * is synchronised once, after counters[] has been copied to h_info (pinned host memory, UGS_CTR_COUNT int64):
+ * h_info[UGS_CTR_TOTAL_EDGES] = Ebar; a non-zero h_info[UGS_CTR_UNSORTED] means the batch needs the staged path and no
+ * output is valid. ugs_fused_finish narrows the bound-sized arrays into edge_index_out[2,Ebar] / edge_src_out[Ebar].
+ * Outputs are bit-identical to the staged sequence. */
+int64_t ugs_fused_capacity(int64_t E, int64_t m);
+int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
+                           int64_t total_nodes, int64_t m, int k, int mode, uint64_t seed, uint64_t graph_index_base,
+                           uint64_t sample_index_base, int seed_mode, void* workspace, const ugs_layout* L,
+                           void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
+                           int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info, void* stream);
+int ugs_fused_finish(const int64_t* ei_u, const int64_t* ei_v, const int64_t* ei_src, int64_t total,
+                     int64_t* edge_index_out, int64_t* edge_src_out, void* stream);
 
 /* ---- exact-uniform accept/reject variant (not in the reference, see oracle/uni_oracle.c) ---------
  * ugs_preproc_uniform: call after ugs_preproc_batch. Replaces order / suffix_deg / suf / bucket_b / cum / Z by

@@ -127,3 +127,10 @@ __device__ __forceinline__ double root_x(u32 w0, u32 w1, double Z) {
     u64 u53 = ((((u64)w0) << 32) | (u64)w1) >> 11;
     return ((double)u53 * (1.0 / 9007199254740992.0)) * Z;
 }
+
+// internal entry points shared between translation units
+int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                          uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                          int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
+                          void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
+                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh);

@@ -407,25 +407,40 @@ __device__ void block_sort_u64(u64* gkeys, int n, u64* smem_buf) {
 }
 
 // Block-wide exclusive scan over n values produced by f(i), written through out(i, excl); returns total.
-// Each thread owns a contiguous segment, the per-thread sums are scanned through shared memory.
+// Each thread owns a contiguous segment; the per-thread sums are scanned with warp shuffles (two levels: inside every
+// warp, then over the warp totals), not by one thread walking all of them. For doubles the callers only rely on the
+// result when every partial sum is an exactly representable integer, so the association order does not matter.
 template <typename T, typename F, typename O>
 __device__ T block_exclusive_scan(int n, F f, O out, T* sm /* blockDim.x + 1 */) {
     const int T_ = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T_ >> 5;
     const int seg = (n + T_ - 1) / T_;
     const int b = threadIdx.x * seg, e = min(n, b + seg);
     T local = 0;
     for (int i = b; i < e; ++i) local += f(i);
-    sm[threadIdx.x] = local;
+    T incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const T y = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) sm[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        T run = 0;
-        for (int t = 0; t < T_; ++t) { T v = sm[t]; sm[t] = run; run += v; }
-        sm[T_] = run;
+    if (warp == 0) {
+        const T v = (lane < nw) ? sm[lane] : (T)0;
+        T wi = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const T y = __shfl_up_sync(FULL_MASK, wi, off);
+            if (lane >= off) wi += y;
+        }
+        if (lane < nw) sm[32 + lane] = wi - v;  // exclusive prefix of the warp totals
+        if (lane == 31) sm[64] = wi;            // grand total (nw <= 32)
     }
     __syncthreads();
-    T run = sm[threadIdx.x];
+    T run = sm[32 + warp] + (incl - local);
     for (int i = b; i < e; ++i) { T v = f(i); out(i, run); run += v; }
-    const T total = sm[T_];
+    const T total = sm[64];
     __syncthreads();
     return total;
 }
@@ -435,11 +450,12 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
                   i64 node_base, int k, const i64* __restrict__ perm, i64 n_general, WS w) {
     __shared__ u64 sbuf[GEN_SORT_SMEM];
     __shared__ double sscan[GEN_THREADS + 1];
-    __shared__ int s_cnt[4];
+    __shared__ int s_cnt[5];  // [4]: the graph has a self-loop column
     const int tid = threadIdx.x, T_ = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T_ >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
 
+    if (n_general < 0) n_general = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path: count stays on the device
     for (i64 item = blockIdx.x; item < n_general; item += gridDim.x) {
         const i64 g = w.glist[item];
         const i64 lo = ptr[g];
@@ -459,13 +475,13 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
 
         // ---- A.2 degrees (iof = degree, ord = cursor) -------------------------------------------
         for (int v = tid; v < n; v += T_) { iof[v] = 0; ord[v] = 0; }
-        if (tid < 4) s_cnt[tid] = 0;
+        if (tid < 5) s_cnt[tid] = 0;
         __syncthreads();
         for (i64 c = tid; c < nc; c += T_) {
             const i64 j = perm ? perm[c0 + c] : c0 + c;
             const i64 u = row0[j] - lo, v = row1[j] - lo;
             if (u < 0 || u >= n) { atomicOr(&w.counters[UGS_CTR_UNSORTED], 8ull); continue; }
-            if (v >= 0 && v < n) { atomicAdd(&iof[u], 1); atomicAdd(&iof[v], 1); }
+            if (v >= 0 && v < n) { atomicAdd(&iof[u], 1); atomicAdd(&iof[v], 1); if (u == v) s_cnt[4] = 1; }
         }
         __syncthreads();
         {
@@ -592,33 +608,43 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
             }
         }
         __syncthreads();
-        // ---- A.4 suffix degree: one warp per position --------------------------------------------
+        // ---- A.4 suffix degree + reachability. Both walk rows and look up the position of every neighbour: when the
+        //      graph fits (PROTEINS-sized graphs always do), neighbour ids and positions are staged in shared memory as
+        //      16-bit values first, so that a step of the bounded BFS costs shared-memory instead of L2 latency.
+        unsigned short* s_idx = reinterpret_cast<unsigned short*>(sbuf);   // [nnz]  (sort buffer, idle by now)
+        unsigned short* s_iof = reinterpret_cast<unsigned short*>(sscan);  // [n]
+        const bool staged = (nnz <= GEN_SORT_SMEM * 4) && (n <= GEN_THREADS * 4);
+        if (staged) {
+            for (int p = tid; p < nnz; p += T_) s_idx[p] = (unsigned short)cidx[p];
+            for (int v = tid; v < n; v += T_) s_iof[v] = (unsigned short)iof[v];
+        }
+        __syncthreads();
         for (int vi = warp; vi < n; vi += nwarps) {
             const int v = ord[vi];
             const u32 p0 = rp[v], p1 = rp[v + 1];
             int cnt = 0;
-            for (u32 p = p0 + lane; p < p1; p += 32) cnt += (iof[cidx[p]] >= vi) ? 1 : 0;
+            if (staged) { for (u32 p = p0 + lane; p < p1; p += 32) cnt += ((int)s_iof[s_idx[p]] >= vi) ? 1 : 0; }
+            else { for (u32 p = p0 + lane; p < p1; p += 32) cnt += (iof[cidx[p]] >= vi) ? 1 : 0; }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(FULL_MASK, cnt, off);
             if (lane == 0) sdg[vi] = cnt;
-        }
-        __syncthreads();
-        // ---- reachability (component of v in the suffix graph has >= k vertices) + weight ---------
-        for (int vi = warp; vi < n; vi += nwarps) {
-            const int v = ord[vi];
-            const int sd = sdg[vi];
+            // ---- reachability (component of v in the suffix graph has >= k vertices) + weight -------
+            const int sd = cnt;
             bool reach = (k <= 1);
             if (!reach && sd > 0) {
                 int q = (lane == 0) ? v : -1;  // lane j holds queue[j]
                 int qn = 1;
                 for (int h = 0; h < qn && !reach; ++h) {
                     const int u = __shfl_sync(FULL_MASK, q, h);
-                    const u32 p0 = rp[u], p1 = rp[u + 1];
-                    for (u32 pb = p0; pb < p1 && !reach; pb += 32) {
+                    const u32 q0 = rp[u], q1 = rp[u + 1];
+                    for (u32 pb = q0; pb < q1 && !reach; pb += 32) {
                         const u32 p = pb + lane;
                         int x = -1;
                         bool ok = false;
-                        if (p < p1) { x = cidx[p]; ok = (iof[x] >= vi); }
+                        if (p < q1) {
+                            if (staged) { x = s_idx[p]; ok = ((int)s_iof[x] >= vi); }
+                            else { x = cidx[p]; ok = (iof[x] >= vi); }
+                        }
                         for (int j = 0; j < qn; ++j) {
                             const int qj = __shfl_sync(FULL_MASK, q, j);  // every lane must take part
                             ok = ok && (x != qj);
@@ -626,14 +652,14 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
                         const u32 peers = __match_any_sync(FULL_MASK, ok ? x : (-1 - lane));
                         ok = ok && ((peers & lt_mask) == 0);
                         const u32 ball = __ballot_sync(FULL_MASK, ok);
-                        const int cnt = __popc(ball);
-                        if (qn + cnt >= k) { reach = true; break; }
-                        // append: destination lane j in [qn, qn+cnt) takes the (j-qn)-th newcomer
+                        const int c = __popc(ball);
+                        if (qn + c >= k) { reach = true; break; }
+                        // append: destination lane j in [qn, qn+c) takes the (j-qn)-th newcomer
                         const int t = lane - qn;
-                        const int src = (t >= 0 && t < cnt) ? select_bit32(ball, t) : 0;
+                        const int src = (t >= 0 && t < c) ? select_bit32(ball, t) : 0;
                         const int xs = __shfl_sync(FULL_MASK, x, src);
-                        if (t >= 0 && t < cnt) q = xs;
-                        qn += cnt;
+                        if (t >= 0 && t < c) q = xs;
+                        qn += c;
                     }
                 }
             }
@@ -710,7 +736,8 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
             ugs_ginfo gi;
             gi.Z = Z; gi.nnz = nnz; gi.level = level;
             gi.n_eligible = (level == 0) ? n0 : (level == 1 ? n1 : n);
-            gi.last_viable = lastv; gi.mult = 0; gi.cls = 2;
+            gi.last_viable = lastv; gi.cls = 2;
+            gi.mult = s_cnt[4] ? 0 : -1;  // general path: -1 = no self-loop column (symmetric multigraph rows)
             w.ginfo[g] = gi;
         }
         __syncthreads();
@@ -843,6 +870,8 @@ extern "C" int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, con
     WS w = ws_views(workspace, L);
     const int64_t* row0 = edge_index;
     const int64_t* row1 = edge_index ? edge_index + E : nullptr;
+    // n_general / n_large < 0: the counts are not known on the host (fused small-batch path, ugs_sample_batch_fused): the
+    // kernels are launched with grids sized for the worst case and read the counts from counters[] themselves.
     if ((parts & UGS_PREPROC_SMALL) && n_general < G) {
         constexpr int WARPS = 8;
         k_preproc_small<WARPS><<<(unsigned)((G + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(
@@ -850,15 +879,16 @@ extern "C" int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, con
         UGS_LAUNCH_CHECK("k_preproc_small");
     }
     if (!(parts & UGS_PREPROC_GENERAL)) return UGS_OK;
-    if (n_large > 0) {
+    if (n_large != 0) {
         const int rc = ugs_launch_preproc_large(row0, row1, ptr, node_base, k, perm, n_large, w, st);
         if (rc != UGS_OK) return rc;
     }
-    if (n_general > n_large) {
+    if (n_general < 0 || n_general > n_large) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned grid = (unsigned)(n_general < (int64_t)sms ? n_general : sms);
+        const int64_t bound = n_general < 0 ? G : n_general;
+        const unsigned grid = (unsigned)(bound < (int64_t)sms ? bound : sms);
         k_preproc_general<<<grid, GEN_THREADS, 0, st>>>(row0, row1, ptr, node_base, k, perm, n_general, w);
         UGS_LAUNCH_CHECK("k_preproc_general");
     }

@@ -79,9 +79,10 @@ k_preproc_large(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
     const u32 lt_mask = (1u << lane) - 1u;
     const i64 gtid = (i64)blockIdx.x * T_ + tid, gsize = (i64)gridDim.x * T_;
     const i64 gwarp = gtid >> 5, gwarps = gsize >> 5;
-    unsigned long long* ctr = w.counters;     // [10] long-row list length, [11] n0, [12] n1, [13] last viable + 1
+    unsigned long long* ctr = w.counters;     // [10] long-row list length, [11] n0, [12] n1, [13] last viable + 1, [14] self-loop flag
     double* lsc = w.lscratch;                 // [0..gridDim) CTA totals, [4095] approximate sum of the weights
 
+    if (n_large < 0) n_large = (i64)ctr[UGS_CTR_N_LARGE];  // fused small-batch path: the count stays on the device
     for (i64 item = 0; item < n_large; ++item) {
         const i64 g = w.llist[item];
         const i64 lo = ptr[g];
@@ -100,13 +101,13 @@ k_preproc_large(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
 
         // ---- A.2 degrees (iof = degree, ord = fill cursor) -------------------------------------------
         for (i64 v = gtid; v < n; v += gsize) { iof[v] = 0; ord[v] = 0; }
-        if (gtid == 0) { ctr[10] = 0; ctr[11] = 0; ctr[12] = 0; ctr[13] = 0; lsc[4095] = 0.0; }
+        if (gtid == 0) { ctr[10] = 0; ctr[11] = 0; ctr[12] = 0; ctr[13] = 0; ctr[14] = 0; lsc[4095] = 0.0; }
         grid.sync();
         for (i64 c = gtid; c < nc; c += gsize) {
             const i64 j = perm ? perm[c0 + c] : c0 + c;
             const i64 u = row0[j] - lo, v = row1[j] - lo;
             if (u < 0 || u >= n) { atomicOr(&ctr[UGS_CTR_UNSORTED], 8ull); continue; }
-            if (v >= 0 && v < n) { atomicAdd(&iof[u], 1); atomicAdd(&iof[v], 1); }
+            if (v >= 0 && v < n) { atomicAdd(&iof[u], 1); atomicAdd(&iof[v], 1); if (u == v) ctr[14] = 1ull; }
         }
         grid.sync();
         int nnz;
@@ -205,24 +206,66 @@ k_preproc_large(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
             }
         }
         grid.sync();
-        // ---- A.3 order: global bitonic network over (degree << 32 | id), grid barrier per stage ----------
+        // ---- A.3 order: bitonic network over (degree << 32 | id). Sub-stages whose partner distance is below
+        //      LG_SORT_SMEM stay inside one chunk of the keys and run in shared memory without a grid barrier; only
+        //      the flips / strides that cross chunks touch global memory, one grid barrier each (n = 10^5: 28 barriers
+        //      instead of 153).
         {
             u64* keys = reinterpret_cast<u64*>(cm);
+            constexpr int C = LG_SORT_SMEM;
+            const int nchunks = (n + C - 1) / C;
             for (i64 v = gtid; v < n; v += gsize) keys[v] = (((u64)(u32)iof[v]) << 32) | (u32)v;
             grid.sync();
-            for (int k2 = 2; (k2 >> 1) < n; k2 <<= 1) {
+            // chunk-local part of stage k2 (all of it when k2 <= C, else the strides below C), keys padded with +inf
+            auto local_stages = [&](int k2_first, int k2_last) {
+                for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+                    const int base = c * C;
+                    for (int i = tid; i < C; i += T_) sbuf[i] = (base + i < n) ? keys[base + i] : ~0ull;
+                    __syncthreads();
+                    for (int k2 = k2_first; k2 <= k2_last; k2 <<= 1) {
+                        int j = k2 >> 1;
+                        if (k2 <= C) {  // flip inside the chunk
+                            for (int t = tid; t < C / 2; t += T_) {
+                                const int blk = t / j, off = t - blk * j;
+                                const int a = blk * k2 + off, b = blk * k2 + k2 - 1 - off;
+                                const u64 x = sbuf[a], y = sbuf[b];
+                                if (y < x) { sbuf[a] = y; sbuf[b] = x; }
+                            }
+                            __syncthreads();
+                            j >>= 1;
+                        } else {
+                            j = C >> 1;  // the flip and the strides >= C were done in global memory
+                        }
+                        for (; j >= 1; j >>= 1) {
+                            for (int t = tid; t < C / 2; t += T_) {
+                                const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), b = a | j;
+                                const u64 x = sbuf[a], y = sbuf[b];
+                                if (y < x) { sbuf[a] = y; sbuf[b] = x; }
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    for (int i = tid; i < C; i += T_) if (base + i < n) keys[base + i] = sbuf[i];
+                    __syncthreads();
+                }
+            };
+            local_stages(2, C);  // every stage up to k2 = C in one go
+            grid.sync();
+            for (int k2 = 2 * C; (k2 >> 1) < n; k2 <<= 1) {
                 for (i64 i = gtid; i < n; i += gsize) {
                     const i64 p = i ^ (i64)(k2 - 1);
                     if (p > i && p < n) { const u64 x = keys[i], y = keys[p]; if (y < x) { keys[i] = y; keys[p] = x; } }
                 }
                 grid.sync();
-                for (int j = k2 >> 2; j >= 1; j >>= 1) {
+                for (int j = k2 >> 2; j >= C; j >>= 1) {
                     for (i64 i = gtid; i < n; i += gsize) {
                         const i64 p = i ^ (i64)j;
                         if (p > i && p < n) { const u64 x = keys[i], y = keys[p]; if (y < x) { keys[i] = y; keys[p] = x; } }
                     }
                     grid.sync();
                 }
+                local_stages(k2, k2);
+                grid.sync();
             }
             for (i64 vi = gtid; vi < n; vi += gsize) {
                 const int v = (int)(u32)keys[vi];
@@ -336,7 +379,8 @@ k_preproc_large(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
             ugs_ginfo gi;
             gi.Z = Z; gi.nnz = nnz; gi.level = level;
             gi.n_eligible = (level == 0) ? n0 : (level == 1 ? n1 : n);
-            gi.last_viable = lastv; gi.mult = 0; gi.cls = 2;
+            gi.last_viable = lastv; gi.cls = 2;
+            gi.mult = ctr[14] ? 0 : -1;  // general path: -1 = no self-loop column
             w.ginfo[g] = gi;
         }
         grid.sync();

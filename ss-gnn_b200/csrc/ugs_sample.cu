@@ -264,11 +264,16 @@ __device__ __forceinline__ int warp_cdf_search(const double* __restrict__ cm, in
     return ball ? lo + __ffs(ball) - 1 : n - 1;
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef GEN_MINB
+#define GEN_MINB 5  // resident CTAs per SM the kernel is compiled for (51 registers -> 40 warps per SM)
+#endif
+__global__ void __launch_bounds__(256, GEN_MINB)
 k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
                  int seed_mode, i64 n_general, int bm_words, int bm_stride, WS w, i64* __restrict__ nodes_out,
                  i64* __restrict__ edge_ptr) {
     extern __shared__ __align__(16) u32 bm_all[];
+    if (n_general < 0) n_general = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
+    if (n_general == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     u32* bm = bm_all + (size_t)warp * bm_stride;  // [bm_words] cut bitmap (bm_words is a multiple of 32)
     u32* bc = bm + bm_words;                      // [bm_words / 32] set bits per block of 32 words
@@ -277,12 +282,14 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
     const i64 total = n_general * m;
     unsigned long long n_incomplete = 0, n_relaxed = 0, n_entries = 0;
 
+    // a claim covers GEN_WORK_CHUNK samples when there is plenty of work, one sample when every warp gets only a few
+    const int chunk = (total >= (i64)gridDim.x * (blockDim.x >> 5) * (2 * GEN_WORK_CHUNK)) ? GEN_WORK_CHUNK : 1;
     while (true) {
         i64 tbase = 0;
-        if (lane == 0) tbase = (i64)atomicAdd(&w.counters[UGS_CTR_WORK], (unsigned long long)GEN_WORK_CHUNK);
+        if (lane == 0) tbase = (i64)atomicAdd(&w.counters[UGS_CTR_WORK], (unsigned long long)chunk);
         tbase = __shfl_sync(FULL_MASK, tbase, 0);
         if (tbase >= total) break;
-        const i64 tend = min(total, tbase + GEN_WORK_CHUNK);
+        const i64 tend = min(total, tbase + chunk);
     for (i64 t = tbase; t < tend; ++t) {
         const i64 gi_ = t / m;
         const i64 i = t - gi_ * m;
@@ -392,12 +399,22 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
         int cntE = 0;
         if (size == k) {
             if (lane < size) atomicOr(&bm[mine >> 5], 1u << (mine & 31));
+            // A graph without self-loop columns (mult < 0) is a symmetric multigraph: v appears in row(u) as often as u in
+            // row(v). The entries of the LONGEST member row that point into S are therefore counted from the other
+            // members' rows (entries equal to that member) and the long row -- typically a hub -- is not walked at all.
+            int skip = -1, hub = -1;
+            if (gi.mult < 0) {
+                const u32 key = (lane < size) ? (((my_p1 - my_p0) << 5) | (u32)lane) : 0u;
+                const u32 best = __reduce_max_sync(FULL_MASK, key);
+                if ((best >> 5) > 64u) { skip = (int)(best & 31u); hub = __shfl_sync(FULL_MASK, mine, skip); }
+            }
             __syncwarp();
             for (int j = 0; j < size; ++j) {
+                if (j == skip) continue;
                 const u32 p0 = __shfl_sync(FULL_MASK, my_p0, j), p1 = __shfl_sync(FULL_MASK, my_p1, j);
                 for (u32 p = p0 + lane; p < p1; p += 32) {
                     const int y = cidx[p];
-                    cntE += (int)((bm[y >> 5] >> (y & 31)) & 1u);
+                    cntE += (int)((bm[y >> 5] >> (y & 31)) & 1u) + (y == hub ? 1 : 0);
                 }
             }
             cntE = __reduce_add_sync(FULL_MASK, cntE);
@@ -813,12 +830,27 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
 // =====================================================================================================
 // General path: emission, one warp per sample (also the generic counter for caller-provided rows)
 // =====================================================================================================
+// Rows are walked 32 entries at a time. Membership and local index of an entry come from a 1024-slot table in shared
+// memory (slot y & 1023 holds the position of member y inside the sample, 0xFF = empty) followed by ONE shuffle that
+// fetches the candidate member for an exact comparison: a chunk without a possible member costs a load, a table
+// look-up and a vote; a hub row of thousands of entries holds a handful of members. Two members that share a slot
+// (rare: ~k^2/2048 of the samples) make the sample fall back to comparing against all k members.
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(256)
 k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mode, i64 n_items, bool use_glist,
                WS w, const i64* __restrict__ nodes, i64* __restrict__ edge_ptr, i64 total,
                i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
+    __shared__ __align__(16) unsigned char pos_all[8][1024];
+    if (n_items < 0) n_items = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
+    if (n_items == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    unsigned char* pos = pos_all[warp];
+    {
+        uint4* p4 = reinterpret_cast<uint4*>(pos);
+        p4[lane] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        p4[lane + 32] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncwarp();
     const u32 lt_mask = (1u << lane) - 1u;
     const i64 nwarps = (i64)gridDim.x * wpb;
     const i64 total_items = n_items * m;
@@ -836,22 +868,35 @@ k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mod
         }
         const i64 lo = ptr[g];
         const i64 nb = lo - node_base;
-        const u32* rp = w.rowptr + nb + g;
-        const i32* cidx = w.csr_idx + 2 * w.cstart[g];
-        const i32* ccol = w.csr_col + 2 * w.cstart[g];
+        const u32* __restrict__ rp = w.rowptr + nb + g;
+        const i32* __restrict__ cidx = w.csr_idx + 2 * w.cstart[g];
+        const i32* __restrict__ ccol = w.csr_col + 2 * w.cstart[g];
         const i64 nv = (lane < k) ? nodes[sidx * k + lane] : 0;
         const bool complete = !__any_sync(FULL_MASK, (lane < k) && nv < 0);
         const int mine = (lane < k && nv >= 0) ? (int)(nv - lo) : -1;
         i64 cnt = 0;
         if (complete) {
+            // members sharing a table slot (or equal members in caller-provided rows): compare against all k instead
+            const u32 peers = __match_any_sync(FULL_MASK, (lane < k) ? (mine & 1023) : (0x10000 + lane));
+            const bool clash = __any_sync(FULL_MASK, (lane < k) && (peers != (1u << lane)));
+            if (lane < k && !clash) pos[mine & 1023] = (unsigned char)lane;
+            const u32 my_p0 = (lane < k) ? rp[mine] : 0u, my_p1 = (lane < k) ? rp[mine + 1] : 0u;
+            __syncwarp();
             for (int j = 0; j < k; ++j) {
                 const int u = __shfl_sync(FULL_MASK, mine, j);
-                const u32 p0 = rp[u], p1 = rp[u + 1];
+                const u32 p0 = __shfl_sync(FULL_MASK, my_p0, j), p1 = __shfl_sync(FULL_MASK, my_p1, j);
                 for (u32 pb = p0; pb < p1; pb += 32) {
                     const u32 p = pb + lane;
                     int y = -2, l = -1;
                     if (p < p1) y = cidx[p];
-                    for (int q = 0; q < k; ++q) if (y == __shfl_sync(FULL_MASK, mine, q)) l = q;
+                    if (!clash) {
+                        const int c = (p < p1) ? (int)pos[y & 1023] : 0xFF;
+                        if (!__any_sync(FULL_MASK, c != 0xFF)) continue;
+                        const int cand = __shfl_sync(FULL_MASK, mine, c & 31);
+                        if (c != 0xFF && cand == y) l = c;
+                    } else {
+                        for (int q = 0; q < k; ++q) if (y == __shfl_sync(FULL_MASK, mine, q)) l = q;
+                    }
                     const bool hit = (l >= 0) && (p < p1);
                     const u32 ball = __ballot_sync(FULL_MASK, hit);
                     if (!COUNT_ONLY && hit) {
@@ -866,6 +911,9 @@ k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mod
                     cnt += __popc(ball);
                 }
             }
+            __syncwarp();
+            if (lane < k && !clash) pos[mine & 1023] = (unsigned char)0xFF;
+            __syncwarp();
         }
         if (COUNT_ONLY && lane == 0) edge_ptr[1 + sidx] = cnt;
     }
@@ -912,9 +960,14 @@ int ugs_run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& 
     return run_scan(edge_ptr, B, scratch, scratch_bytes, w, st);
 }
 
-static inline void small_items(int64_t m, int* tiles_per_item, int64_t* items_per_graph) {
+// A warp handles up to 4 tiles of 32 samples of one graph (the graph's tables are staged once per warp). Small batches
+// do not have enough (graph, 4-tile) items to fill the GPU -- MUTAG-shaped G=188, m=64: 188 warps on 148 SMs -- so
+// they get fewer tiles per warp until there are at least two 8-warp CTAs per SM.
+static inline void small_items(int64_t m, int64_t G, int* tiles_per_item, int64_t* items_per_graph) {
     const int64_t ntiles = (m + 31) / 32;
     int tpi = (int)(ntiles < 4 ? (ntiles < 1 ? 1 : ntiles) : 4);
+    const int64_t want = (int64_t)sm_count() * 16;
+    while (tpi > 1 && G * ((ntiles + tpi - 1) / tpi) < want) tpi >>= 1;
     *tiles_per_item = tpi;
     *items_per_graph = (ntiles + tpi - 1) / tpi;
     if (*items_per_graph < 1) *items_per_graph = 1;
@@ -935,6 +988,18 @@ extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t nod
                                       int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
                                       void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
                                       int64_t* sample_ptr, int64_t* h_info, void* stream_) {
+    return ugs_sample_batch_impl(ptr, G, node_base, m, k, seed, graph_index_base, sample_index_base, seed_mode, variant,
+                                 n_general, max_n_general, workspace, L, scratch, scratch_bytes, nodes, edge_ptr,
+                                 sample_ptr, h_info, stream_, false);
+}
+
+// counters_fresh: ugs_segment_batch has just zeroed all of counters[] on this stream and nothing has counted since
+// (the fused small-batch path): the two counter memsets are skipped.
+int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
+                          uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
+                          int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
+                          void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
+                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh) {
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (h_info && variant != UGS_VARIANT_REF) return ugs_set_error(UGS_EINVAL, "the early read-back needs UGS_VARIANT_REF");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
@@ -950,8 +1015,10 @@ extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t nod
     const u32 ibase = (u32)sample_index_base;
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
-    UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64) * 4, st));
-    UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_EARLY_TOTAL], 0, sizeof(i64) * UGS_CTR_EARLY_SLOTS, st));
+    if (!counters_fresh) {
+        UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_TOTAL_EDGES], 0, sizeof(i64) * 4, st));
+        UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_EARLY_TOTAL], 0, sizeof(i64) * UGS_CTR_EARLY_SLOTS, st));
+    }
     if (G <= 0 || m == 0) {
         if (h_info) {  // nothing is sampled: the snapshot is all the caller needs
             const int rc = ugs_batch_info_begin(workspace, L, h_info, stream_);
@@ -971,7 +1038,7 @@ extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t nod
         return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
     }
     int tpi; int64_t ipg;
-    small_items(m, &tpi, &ipg);
+    small_items(m, G, &tpi, &ipg);
     // packed node rows for the emission pass (k <= 8), kept behind the scan words of the caller's scratch buffer
     u64* packed = nullptr;
     if (k <= 8 && scratch && scratch_bytes >= ugs_sample_scratch_bytes(G, m))
@@ -993,7 +1060,7 @@ extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t nod
 #undef UGS_LAUNCH_SAMPLE
         UGS_LAUNCH_CHECK("k_sample_small");
     }
-    if (n_general > 0) {
+    if (n_general != 0) {  // < 0: count on the device, max_n_general = the caller's bound (total nodes of the batch)
         // per-warp slice: cut bitmap padded to whole blocks of 32 words + one count per block (16-byte aligned)
         const int bm_words = (int)(((max_n_general + 1023) / 1024) * 32);
         const int bm_stride = bm_words + ((bm_words / 32 + 3) & ~3);
@@ -1005,8 +1072,10 @@ extern "C" int ugs_sample_batch_early(const int64_t* ptr, int64_t G, int64_t nod
             return ugs_set_error(UGS_ELIMIT, "graph with %lld nodes exceeds the per-warp cut bitmap (max %zu nodes)",
                                  (long long)max_n_general, smem_cap * 8);
         UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_general, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
         UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_WORK], 0, sizeof(i64), st));
-        const int64_t total = n_general * m;
+        const int64_t total = (n_general < 0 ? G : n_general) * m;
         int64_t blocks = (total + wpb - 1) / wpb;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
@@ -1071,7 +1140,7 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
         packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
     if (n_general < G) {
         int tpi; int64_t ipg;
-        small_items(m, &tpi, &ipg);
+        small_items(m, G, &tpi, &ipg);
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS);
         if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
@@ -1087,8 +1156,8 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
         }
         UGS_LAUNCH_CHECK("k_emit_small");
     }
-    if (n_general > 0) {
-        int64_t blocks = (n_general * m + 7) / 8;
+    if (n_general != 0) {
+        int64_t blocks = ((n_general < 0 ? G : n_general) * m + 7) / 8;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         k_emit_general<false><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, mode, n_general, true, w, nodes,

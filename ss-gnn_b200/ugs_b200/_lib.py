@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_fused.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -24,6 +24,7 @@ EXPORTS = [
     "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
     "ugs_wire_bytes", "ugs_pack_outputs", "ugs_pack_status", "ugs_fetch_outputs", "ugs_emit_edges_packed", "ugs_sample_batch_early",
+    "ugs_fused_capacity", "ugs_sample_batch_fused", "ugs_fused_finish",
 ]
 
 
@@ -128,6 +129,11 @@ def lib():
     L.ugs_preproc_batch_parts.argtypes = [vp, i64, vp, i64, i64, ci, vp, i64, i64, ci, vp, LP, vp]
     L.ugs_emit_edges_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, i64, vp, LP, vp, vp, i64, vp, vp, vp, sz, vp]
     L.ugs_sample_batch_early.argtypes = [vp, i64, i64, i64, ci, u64, u64, u64, ci, ci, i64, i64, vp, LP, vp, sz, vp, vp, vp, vp, vp]
+    L.ugs_fused_capacity.restype = i64
+    L.ugs_fused_capacity.argtypes = [i64, i64]
+    L.ugs_sample_batch_fused.argtypes = [vp, i64, vp, i64, i64, i64, i64, ci, ci, u64, u64, u64, ci, vp, LP, vp, sz,
+                                         vp, vp, vp, vp, vp, vp, i64, vp, vp]
+    L.ugs_fused_finish.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.ugs_wire_bytes.restype = sz
     L.ugs_wire_bytes.argtypes = [i64, ci, i64, ci, ci]
     L.ugs_pack_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, ci, vp, vp]

@@ -274,11 +274,19 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
         p = ptr.to(dev, non_blocking=True)
         # UGS_B200_VARIANT=uniform selects the exact-uniform accept/reject mode; default = reference law
         variant = os.environ.get("UGS_B200_VARIANT", "ref").lower()
-        b = _engine.DeviceBatch(ei, p, int(k), pb[0], pb[1] - pb[0], variant=variant)
-        outs, _stats = b.sample(int(m_per_graph), int(k), mode, int(seed))
+        r = None
+        G, E, NT = int(p.numel()) - 1, int(ei.size(1)) if ei.dim() == 2 else 0, pb[1] - pb[0]
+        if (variant == "ref" and not _debug_on() and ei.dim() == 2 and ei.size(0) == 2
+                and _engine.fused_eligible(E, G, NT, int(m_per_graph), int(k))):
+            # DataLoader-sized call: the whole pipeline as one library call with one host round trip
+            r = _engine.sample_batch_fused(ei, p, int(m_per_graph), int(k), mode, int(seed), pb[0], NT)
+        if r is None:
+            b = _engine.DeviceBatch(ei, p, int(k), pb[0], NT, variant=variant)
+            r = b.sample(int(m_per_graph), int(k), mode, int(seed))
+            if _debug_on():
+                _debug_report(b, r[0][0], int(m_per_graph), int(k), with_cache_line=True)
+        outs, _stats = r
         sample_batch.last_stats = _stats
-        if _debug_on():
-            _debug_report(b, outs[0], int(m_per_graph), int(k), with_cache_line=True)
         return tuple(outs if _want_cuda_out(edge_index) else _to_host_batch(outs, mode, int(k)))
 
 
