@@ -229,6 +229,122 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+# Every BASELINE.json config (and the trainer's mini-batch sizes) next to the headline workload
+# ---------------------------------------------------------------------------------------------------------
+CONFIG_CASES = [
+    # name, generator, graphs, k, m, BASELINE config it belongs to
+    ("mutag", ("batch", "mutag", 188), 6, 64, "configs[0] MUTAG-shaped, G=188"),
+    ("proteins", ("batch", "proteins", 1113), 6, 100, "configs[1] PROTEINS-shaped, G=1113"),
+    ("minibatch_32", ("batch", "proteins", 32), 6, 100, "configs[1] as the trainer calls it: one DataLoader mini-batch of 32 graphs"),
+    ("minibatch_1024", ("batch", "proteins", 1024), 6, 100, "configs[1], mini-batch of 1024 graphs"),
+    ("qm9_k4", ("batch", "qm9", 131072), 4, 10, "configs[2] QM9-shaped, k=4, m=10"),
+    ("qm9_k5", ("batch", "qm9", 131072), 5, 10, "configs[2] QM9-shaped, k=5, m=10"),
+    ("powerlaw_1e4", ("ba", 10000), 6, 20000, "configs[4] Barabasi-Albert n=10^4, one graph"),
+    ("powerlaw_1e5", ("ba", 100000), 6, 20000, "configs[4] Barabasi-Albert n=10^5, one graph"),
+]
+
+
+def _gen_case(gen, seed):
+    from ugs_b200 import synth
+    if gen[0] == "ba":
+        return synth.barabasi_albert(gen[1], 3, seed)
+    return synth.make_batch(gen[1], gen[2], seed)
+
+
+def l2_copy_peak_gbs(torch, dev):
+    """Measured L2 bandwidth of this GPU: device copy of a 24 MB buffer (source + destination stay resident in the 126 MB
+    L2), read + write bytes, best of 20 -- the peak the general-path ("l2"-bound) kernels are reported against."""
+    a = torch.empty(24 << 20, dtype=torch.uint8, device=dev)
+    b = torch.empty_like(a)
+    for _ in range(5):
+        b.copy_(a)
+    best = 0.0
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        e1.synchronize()
+        best = max(best, 2 * a.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
+def run_config_cases(torch, dev, flush_buf, peak_hbm, with_reference=True, steps=10):
+    """device-resident whole-call time (CUDA events, L2 flushed between calls), end-to-end time through
+    ugs_sampler.sample_batch with pageable CPU tensors (what gps/experiment.py:877-883 passes), and the reference's own
+    sample_batch on the same batch on one host core (it is single-threaded), for every BASELINE config."""
+    import ugs_sampler
+    from ugs_b200.engine import sample_batch_device, fused_eligible
+    out = {}
+    ref_mod = None
+    if with_reference:
+        try:
+            from oracle import ref_loader
+            if ref_loader.available("ugs_sampler", "nopin"):
+                ref_mod = ref_loader.load("ugs_sampler", "nopin")
+        except Exception:
+            ref_mod = None
+    for idx, (name, gen, k, m, what) in enumerate(CONFIG_CASES):
+        ei, ptr = _gen_case(gen, 1234 + idx)
+        G, E, NT = len(ptr) - 1, ei.shape[1], int(ptr[-1] - ptr[0])
+        d_ei, d_ptr = torch.from_numpy(ei).to(dev), torch.from_numpy(ptr).to(dev)
+        for w in range(3):
+            outs, st = sample_batch_device(d_ei, d_ptr, m, k, "sample", 5 + w, int(ptr[0]), NT)
+        ts = []
+        for s_ in range(steps):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            outs, st = sample_batch_device(d_ei, d_ptr, m, k, "sample", 100 + s_, int(ptr[0]), NT)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = statistics.median(ts)
+        ebar = st["n_edge_entries"] / max(st["n_graphlets"], 1)
+        b_alg = 8 * k + 8 + 24 * ebar + (16 * E / max(G, 1) + 16) / m
+        del outs
+        # end to end: pageable CPU int64 tensors in, pinned CPU int64 tensors out
+        h_ei, h_ptr = torch.from_numpy(ei), torch.from_numpy(ptr)
+        for w in range(3):
+            ugs_sampler.sample_batch(h_ei, h_ptr, m, k, mode="sample", seed=w)
+        te = []
+        for s_ in range(max(5, steps // 2)):
+            t0 = time.perf_counter()
+            r = ugs_sampler.sample_batch(h_ei, h_ptr, m, k, mode="sample", seed=50 + s_)
+            te.append(time.perf_counter() - t0)
+        del r
+        e2e_ms = 1e3 * statistics.median(te)  # median: the pinned-memory allocator grows on a new output size
+        row = {"what": what, "graphs": G, "nodes": NT, "edge_columns": E, "k": k, "m": m,
+               "device_ms": ms, "graphlets_per_s": G * m / (ms * 1e-3),
+               "path": "fused (one call, one host round trip)" if fused_eligible(E, G, NT, m, k) else "staged",
+               "general_path_graphs": st["n_general_graphs"], "mean_edge_entries_per_graphlet": ebar,
+               "roofline_step": {"bytes_per_graphlet": b_alg, "frac": b_alg * G * m / (ms * 1e-3) / 1e9 / peak_hbm},
+               "e2e_ms": e2e_ms, "e2e_graphlets_per_s": G * m / (e2e_ms * 1e-3)}
+        if ref_mod is not None:
+            # the reference, one core, cold preprocessing cache; big configs: a bounded sample of the same batch
+            g_ref = min(G, 4096)
+            m_ref = min(m, 1000)
+            col_graph = np.searchsorted(ptr, ei[0], side="right") - 1
+            c1 = int(np.searchsorted(col_graph, g_ref))
+            e_ref = torch.from_numpy(np.ascontiguousarray(ei[:, :c1]))
+            p_ref = torch.from_numpy(np.ascontiguousarray(ptr[:g_ref + 1]))
+            t0 = time.perf_counter()
+            for g0 in range(0, g_ref, 256):  # DataLoader-sized calls: the reference's slice step is O(G*E) per call
+                g1 = min(g_ref, g0 + 256)
+                ca, cb = int(np.searchsorted(col_graph, g0)), int(np.searchsorted(col_graph, g1))
+                ref_mod.sample_batch(e_ref[:, ca:cb] - int(ptr[g0]), p_ref[g0:g1 + 1] - int(ptr[g0]), m_ref, k, "sample", 42)
+            t_ref = time.perf_counter() - t0
+            row["reference_cpu"] = {"ms": 1e3 * t_ref, "graphlets_per_s": g_ref * m_ref / t_ref, "cores": 1,
+                                    "sample": f"unmodified reference sample_batch, first {g_ref} graphs, m={m_ref}, "
+                                              f"256 graphs per call, cold cache"}
+            row["speedup_e2e_vs_reference_1core"] = row["e2e_graphlets_per_s"] / row["reference_cpu"]["graphlets_per_s"]
+        out[name] = row
+        del d_ei, d_ptr
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -241,6 +357,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (other BASELINE configs)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained loop (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -313,7 +431,7 @@ def main():
             stage_ms["preproc"].append(e0.elapsed_time(e1))
             stage_ms["sample"].append(e1.elapsed_time(e2))
             stage_ms["emit"].append(e2.elapsed_time(e3))
-        last.update(stats=stats, total=total, n_general=b.n_general)
+        last.update(stats=stats, total=total, n_general=b.n_general, nodes=nodes, eptr=eptr, batch=b)
         return e0.elapsed_time(e3)
 
     clk = ClockSampler(local_rank)
@@ -336,6 +454,21 @@ def main():
     times = [step(1000 + s, True) for s in range(args.steps)]
     barrier()
     launches = int(L.ugs_launch_count()) - launches0
+    # ---- sustained: the same step back to back for >= --sustained-seconds (the headline region above is milliseconds
+    # long, i.e. a burst number); same L2 flush between steps, device-event time of the steps only
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_before = len(stage_ms["emit"])
+        t_wall0 = time.perf_counter()
+        st_times = []
+        while time.perf_counter() - t_wall0 < args.sustained_seconds:
+            st_times.append(step(5000 + len(st_times), True))
+        em = stage_ms["emit"][n_before:]
+        sustained = {"wall_seconds": time.perf_counter() - t_wall0, "steps": len(st_times),
+                     "ms_per_step": sum(st_times) / len(st_times),
+                     "emit_ms": sum(em) / len(em)}
+        for kk in stage_ms:  # keep the headline's stage times those of the K timed steps
+            del stage_ms[kk][n_before:]
     gc.enable()
     t_local = sum(times) / 1e3
     t = torch.tensor([t_local], dtype=torch.float64, device=dev)
@@ -383,6 +516,40 @@ def main():
     emit_ms = sum(stage_ms["emit"]) / len(stage_ms["emit"])
     achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
     step_ms_local = sum(times) / len(times)
+    if sustained is not None:
+        sustained["value"] = st["n_graphlets"] / (sustained["ms_per_step"] * 1e-3)
+        sustained["emit_gbs"] = emit_bytes / (sustained["emit_ms"] * 1e-3) / 1e9
+        sustained["emit_frac_of_peak"] = sustained["emit_gbs"] / peak
+        sustained["what"] = "this rank's steps back to back (L2 flushed between steps, device-event time of the steps)"
+    general = last["n_general"] > 0 and last["n_general"] * 2 >= G - st["n_skipped_graphs"]  # general path dominates
+    stage_avg = {kk: sum(v) / len(v) for kk, v in stage_ms.items()}
+    top_stage = max(stage_avg, key=stage_avg.get)
+    KERNELS = {False: {"preproc": "k_preproc_small (CSR + order + weights, warp per graph)",
+                       "sample": "k_sample_small (+ k_scan_counts)",
+                       "emit": "k_emit_small (induced-edge emission + compaction)"},
+               True: {"preproc": "k_preproc_large / k_preproc_general (cooperative, L2-resident tables)",
+                      "sample": "k_sample_general (+ k_scan_counts)", "emit": "k_emit_general"}}
+    if general:
+        # General path: the graph's tables (CSR, order, CDF: a few MB) live in L2; what the sampling and emission kernels
+        # must move is every member row once per pass (4 B per CSR entry; growth + entry count + emission = 3 passes) and
+        # the outputs. Sum of member-row lengths from the produced node rows (outside the timed region).
+        nodes_l, eptr_l = last["nodes"], last["eptr"]
+        rp = last["batch"].view("rowptr").to(torch.int64)
+        deg = rp[1:NT + 1] - rp[:NT] if G == 1 else None
+        rows_entries = float(deg[(nodes_l.clamp(min=0) - int(ptr_np[0])).reshape(-1)].sum().item()) if deg is not None else 0.0
+        l2_peak = l2_copy_peak_gbs(torch, dev)
+        stage_bytes = {"sample": 2 * 4.0 * rows_entries + (8 * k + 8) * st["n_graphlets"],
+                       "emit": 4.0 * rows_entries + 24.0 * st["n_edge_entries"] + 8 * k * st["n_graphlets"],
+                       "preproc": 16.0 * E + 28.0 * 2 * E + 40.0 * NT}
+        roof = {"bound": "l2", "kernel": KERNELS[True][top_stage], "achieved": stage_bytes[top_stage] / (stage_avg[top_stage] * 1e-3) / 1e9,
+                "peak": l2_peak, "unit": "GB/s", "traffic": None,
+                "peak_source": "measured in this run: device copy of a 24 MB L2-resident buffer, read + write bytes",
+                "algorithmic_bytes_per_launch": stage_bytes[top_stage], "launch_ms": stage_avg[top_stage],
+                "bytes_model": "member rows read once per pass at 4 B per CSR entry (sample: growth + count, emit: 1) + "
+                               "output bytes; preproc: 16 B/column read + CSR/tables written"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+    else:
+        roof = None
     step_achieved = b_alg * st["n_graphlets"] / (step_ms_local * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -414,19 +581,65 @@ def main():
             d2h = int(getattr(ugs_sampler._to_host_batch, "last_d2h_bytes", 0)) or delivered  # bytes that crossed PCIe
             assert not outs[0].is_cuda and outs[0].is_pinned()
         barrier()
-        te = torch.tensor([sum(tt) / 1e3], dtype=torch.float64, device=dev)
+        # the same call with PAGEABLE inputs, which is what the trainer hands over (experiment.py:877-878: .cpu() tensors)
+        p_ei, p_ptr = torch.from_numpy(ei_np), torch.from_numpy(ptr_np)
+        tp_ = []
+        for s in range(2):
+            a, bq = ev(), ev()
+            a.record()
+            outs = ugs_sampler.sample_batch(p_ei, p_ptr, m, k, mode="sample", seed=70 + s)
+            bq.record()
+            bq.synchronize()
+            tp_.append(a.elapsed_time(bq))
+        barrier()
+        # host memory system: what the box's cores can WRITE with streaming stores, measured in this run with the
+        # threads the delivery uses (all ranks at once: they share one memory system), against what the delivery achieved
+        host_peak = None
+        n_thr = ugs_sampler._host_threads()
+        if hasattr(L, "ugs_host_store_bandwidth"):
+            import ctypes
+            L.ugs_host_store_bandwidth.restype = ctypes.c_double
+            L.ugs_host_store_bandwidth.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+            probe = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+            barrier()
+            host_peak = float(L.ugs_host_store_bandwidth(ctypes.c_void_p(probe.data_ptr()), probe.numel(), n_thr, 3))
+            barrier()
+            del probe
+        te = torch.tensor([sum(tt) / 1e3, sum(tp_) / 1e3, host_peak or 0.0], dtype=torch.float64, device=dev)
+        tsum = te.clone()
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": graphlets_step_all * args.e2e_steps / float(te.item()), "unit": UNIT,
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_e2e = float(te[0].item())
+        delivered_all = delivered * world  # every rank delivers its own shard (same shapes up to 0.01 %)
+        e2e = {"value": graphlets_step_all * args.e2e_steps / t_e2e, "unit": UNIT,
                "h2d_bytes_per_step": int(h_ei.numel() * 8 + h_ptr.numel() * 8), "d2h_bytes_per_step": int(d2h),
                "host_bytes_delivered_per_step": int(delivered), "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * t_e2e / args.e2e_steps,
+               "pageable_inputs_value": graphlets_step_all * 2 / float(te[1].item()),
+               "delivery": getattr(ugs_sampler._to_host_batch, "last_delivery", None),
+               "host_threads_per_rank": n_thr,
+               "host_gbs": delivered_all * args.e2e_steps / t_e2e / 1e9,
+               "host_peak_gbs": (float(tsum[2].item()) if host_peak else None),
+               "host_peak_source": "ugs_host_store_bandwidth: 1 GiB of non-temporal stores per rank with the delivery's "
+                                   "thread count, all ranks at the same time, sum over ranks",
                "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu int64 tensors; results cross PCIe packed "
                       "(16-bit deltas per 4096-value block for node ids / source columns, one byte per edge entry) and are "
-                      "widened by host threads while the copy runs"}
+                      "widened by a persistent pool of host threads (AVX-512 / AVX2 non-temporal stores) while the copy "
+                      "runs; bound by host memory bandwidth: host_gbs vs host_peak_gbs"}
         del outs
 
     if rank == 0:
         clk.__exit__(None, None, None)
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and args.workload == "zinc":
+        del d_ei, d_ptr
+        last.clear()
+        torch.cuda.empty_cache()
+        try:
+            configs = run_config_cases(torch, dev, flush_buf, peak, with_reference=not args.no_cpu_baseline)
+        except Exception as ex:  # a report next to the headline, never a reason to lose the headline
+            configs = {"error": repr(ex)[:300]}
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = os.cpu_count() or 1
@@ -452,14 +665,18 @@ def main():
             "ms_per_step_per_rank": per_rank_ms,
             "per_rank": [dict(zip(["ms_per_step", "preproc_ms", "sample_ms", "emit_ms", "slowest_step_ms", "sm_mhz_after"],
                                   [round(v, 4) for v in d])) for d in per_rank_diag],
-            "roofline": {"bound": "hbm", "kernel": "k_emit_small (induced-edge emission + compaction)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms},
+            "roofline": roof if roof is not None else {
+                "bound": "hbm", "kernel": KERNELS[False]["emit"],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
+                "share_of_step": emit_ms / step_ms_local, "dominant_stage": top_stage},
             "roofline_step": {"bytes_per_graphlet": b_alg, "achieved": step_achieved, "peak": peak, "unit": "GB/s",
                               "frac": step_achieved / peak},
+            "sustained": sustained,
             "cpu_baseline": cpu_base,
             "e2e": e2e,
+            "configs": configs,
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "stats_all_ranks": dict(zip(["n_graphlets", "n_edge_entries", "n_incomplete", "n_relaxed_graphs",

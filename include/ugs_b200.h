@@ -25,7 +25,8 @@
  *                                      replaces sampler.cpp:205-280 and the batch driver's
  *                                      post-processing (ugs_sampler_batch_extension.cpp:188-231)
  *
- *   [ugs_pack_outputs + ugs_fetch_outputs]   CPU int64 tensors of the reference ABI, packed across PCIe
+ *   [ugs_deliver_outputs]         CPU int64 tensors of the reference ABI: part by DMA, part packed + widened
+ *   ugs_sample_batch_fused        all of the above in one call for DataLoader-sized batches
  *
  * The other reference samplers (ugs_eps_*, ugs_apx_*, ugs_rwr_*, ugs_enum_*) share the workspace built by the first
  * three calls; ugs_gather_rows / ugs_encoder_offsets, ugs_presample_* and ugs_wl_* cover the callers either side of the
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define UGS_B200_ABI_VERSION 2
+#define UGS_B200_ABI_VERSION 3
 
 /* error codes */
 #define UGS_OK 0
@@ -378,21 +379,31 @@ int ugs_wl_lookup(const uint64_t* digest, const int32_t* num_nodes, int64_t B, c
 
 /* ---- host delivery of the reference's CPU int64 ABI (reference sampler.cpp:190, ugs_sampler_batch_extension.cpp:95) -
  * The reference returns CPU pinned int64 tensors; copying them as they are is PCIe-bound (6.9 GB per ZINC-shaped call).
- * ugs_pack_outputs (device) narrows nodes and edge_src to int32 (delta16 = 0) or to 16-bit deltas against the minimum of
- * their 4096-element block (delta16 = 1; ugs_pack_status tells whether every block fitted, else repack with delta16 = 0)
- * and edge_index to one byte per entry (pairs_u8 = 1: both rows < 16, i.e. mode "sample" with k <= 16) or two int32
- * (pairs_u8 = 0) into d_wire [ugs_wire_bytes(); the delta16 = 0 size is large enough for both];
- * ugs_fetch_outputs copies d_wire to the pinned staging buffer h_wire in chunks and widens every chunk into the final
- * int64 host arrays with n_threads host threads while the next chunks are in flight (blocks until everything has
- * arrived). Values that do not fit the packed format are counted on the device: ugs_fetch_outputs then returns
- * UGS_ELIMIT and the caller copies the int64 tensors as they are. h_edge_index is [2,total] (row 1 at +total). */
-size_t ugs_wire_bytes(int64_t B, int k, int64_t total, int pairs_u8, int delta16);
-int ugs_pack_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index, const int64_t* edge_src,
-                     int64_t total, int pairs_u8, int delta16, void* d_wire, void* stream);
-int ugs_pack_status(const void* d_wire, int64_t B, int k, int64_t total, int pairs_u8, int delta16, int64_t* h_bad,
-                    void* stream);
-int ugs_fetch_outputs(const void* d_wire, void* h_wire, int64_t B, int k, int64_t total, int pairs_u8, int delta16,
-                      int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, void* stream);
+ * ugs_deliver_outputs splits every array between two pipelines that run concurrently:
+ *   DMA    the first dma_fraction of nodes / edge_index rows / edge_src (whole 4096-value blocks) is copied as int64 from
+ *          the device tensors straight into the final host arrays, in slices issued between the wire chunks (no CPU work);
+ *   widen  the rest is packed on the device into d_wire -- nodes and edge_src as 16-bit deltas against the minimum of
+ *          their 4096-value block (int32 when some block spreads too far), edge_index as one byte per entry (pairs_u8 = 1:
+ *          both rows < 16, i.e. mode "sample" with k <= 16) or two int32 --, copied to the pinned staging buffer h_wire
+ *          in chunks, and n_threads host threads (a persistent pool + the caller) widen every chunk into the final arrays
+ *          with non-temporal vector stores while the next chunks are in flight.
+ * Blocks until everything has arrived. dma_fraction = 1 is the plain int64 copy, 0 packs everything (1/7 of the bytes
+ * over PCIe, host-memory bound); the caller chooses by the host threads it owns. d_wire / h_wire: wire_bytes >=
+ * ugs_deliver_wire_bytes(). h_edge_index is [2,total] (row 1 at +total). h_stats (may be NULL): {packed bytes copied, int64
+ * bytes copied by DMA, 1 = 16-bit deltas / 0 = int32, chunks}. UGS_ELIMIT: a value fits neither format (the caller copies
+ * the int64 tensors as they are). ugs_host_store_bandwidth: GB/s of non-temporal stores into dst[bytes] from n_threads
+ * threads of the same pool (best of reps) -- the host-side roofline of the widen pipeline. ugs_host_isa: "avx512" |
+ * "avx2" | "scalar", the widening code chosen for this CPU (UGS_B200_HOST_ISA overrides). */
+size_t ugs_deliver_wire_bytes(int64_t B, int k, int64_t total, int pairs_u8);
+int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index, const int64_t* edge_src,
+                        int64_t total, int pairs_u8, double dma_fraction, void* d_wire, void* h_wire, size_t wire_bytes,
+                        int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, int64_t* h_stats,
+                        void* stream);
+double ugs_host_store_bandwidth(void* dst, size_t bytes, int n_threads, int reps);
+const char* ugs_host_isa(void);
+/* host-only test hook: widen n packed elements with the named code variant ("scalar" | "avx2" | "avx512"; -1 = this CPU
+ * lacks it). kind 0: int32 -> int64, 1 / 2: low / high nibble of a byte -> int64, 3: 16-bit delta + base (0xFFFF -> -1) */
+int ugs_host_widen(int kind, const void* src, int64_t* dst, size_t n, int64_t base, const char* isa);
 
 /* ---- encoder inputs: the gather/offset step right after the sampler -----------------------
  * Reference: SubgraphSamplingGNNClassifier.encode_subgraphs, gps/models/ss_gnn.py:427-471 (same code in

@@ -10,8 +10,8 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_fused.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
-HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(REPO, "include", "ugs_b200.h")]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_hostdeliver.cpp", "ugs_fused.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(CSRC, "ugs_hostio.h"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
     "ugs_abi_version", "ugs_launch_count", "ugs_last_error", "ugs_workspace_layout", "ugs_segment_batch", "ugs_batch_info",
@@ -23,7 +23,8 @@ EXPORTS = [
     "ugs_presample_scratch_bytes", "ugs_presample_plan", "ugs_presample_load",
     "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
-    "ugs_wire_bytes", "ugs_pack_outputs", "ugs_pack_status", "ugs_fetch_outputs", "ugs_emit_edges_packed", "ugs_sample_batch_early",
+    "ugs_deliver_wire_bytes", "ugs_deliver_outputs", "ugs_host_store_bandwidth", "ugs_host_isa", "ugs_host_widen",
+    "ugs_emit_edges_packed", "ugs_sample_batch_early",
     "ugs_fused_capacity", "ugs_sample_batch_fused", "ugs_fused_finish",
 ]
 
@@ -52,10 +53,14 @@ def build(force: bool = False, extra_flags=(), out: str = SO) -> str:
     hdr_t = max(os.path.getmtime(h) for h in HEADERS + [os.path.abspath(__file__)])
     jobs, objs = [], []
     for s in srcs:
-        o = os.path.join(bdir, os.path.basename(s)[:-3] + ".o")
+        o = os.path.join(bdir, os.path.splitext(os.path.basename(s))[0] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
-            jobs.append(["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o])
+            if s.endswith(".cpp"):  # host-only code (thread pool, AVX widening): the host compiler, no nvcc front end
+                jobs.append(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", f"-I{os.path.join(REPO, 'include')}",
+                             f"-I{CSRC}", "-I/usr/local/cuda/include", "-c", s, "-o", o])
+            else:
+                jobs.append(["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(subprocess.check_call, jobs))
@@ -134,11 +139,13 @@ def lib():
     L.ugs_sample_batch_fused.argtypes = [vp, i64, vp, i64, i64, i64, i64, ci, ci, u64, u64, u64, ci, vp, LP, vp, sz,
                                          vp, vp, vp, vp, vp, vp, i64, vp, vp]
     L.ugs_fused_finish.argtypes = [vp, vp, vp, i64, vp, vp, vp]
-    L.ugs_wire_bytes.restype = sz
-    L.ugs_wire_bytes.argtypes = [i64, ci, i64, ci, ci]
-    L.ugs_pack_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, ci, vp, vp]
-    L.ugs_pack_status.argtypes = [vp, i64, ci, i64, ci, ci, ctypes.POINTER(i64), vp]
-    L.ugs_fetch_outputs.argtypes = [vp, vp, i64, ci, i64, ci, ci, vp, vp, vp, ci, vp]
+    L.ugs_deliver_wire_bytes.restype = sz
+    L.ugs_deliver_wire_bytes.argtypes = [i64, ci, i64, ci]
+    L.ugs_deliver_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, cd, vp, vp, sz, vp, vp, vp, ci, vp, vp]
+    L.ugs_host_store_bandwidth.restype = cd
+    L.ugs_host_store_bandwidth.argtypes = [vp, sz, ci, ci]
+    L.ugs_host_isa.restype = ctypes.c_char_p
+    L.ugs_host_widen.argtypes = [ci, vp, vp, sz, i64, ctypes.c_char_p]
     _LIB = L
     return L
 

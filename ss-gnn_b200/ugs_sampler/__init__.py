@@ -124,25 +124,43 @@ def _host_threads() -> int:
     return max(1, min(32, (os.cpu_count() or 1) // local_world))
 
 
+def _dma_fraction(threads: int) -> float:
+    """Share of every output array that travels as plain int64 by DMA (the rest is packed and widened by host threads):
+    UGS_B200_DMA_FRACTION, default 0. Measured on this pool's hosts (profiles/r02_e2e_delivery_{1,8}gpu.txt): the int64
+    result is bound by the HOST memory system either way, and a byte delivered by DMA costs it more than a byte written
+    by a widening thread -- one rank: 54 ms all packed, 69 ms at 0.2, 131 ms all DMA (PCIe-bound); eight ranks: 132 GB/s
+    of int64 all packed against 92 GB/s all DMA. The split is kept for hosts whose cores are the scarcer resource."""
+    env = os.environ.get("UGS_B200_DMA_FRACTION")
+    if env:
+        try:
+            return min(1.0, max(0.0, float(env)))
+        except ValueError:
+            pass
+    return 0.0
+
+
 def _to_host_batch(outs, mode: str, k: int):
     """The 5-tuple (nodes, edge_index, edge_ptr, sample_ptr, edge_src) as CPU pinned int64 tensors (the reference's
-    output contract). Large results travel packed (int32 / one byte per edge entry) and are widened into the final
-    tensors by host threads while the transfer is still running (csrc/ugs_hostio.cu); set UGS_B200_PACKED_D2H=0 to
-    force the plain int64 copy."""
+    output contract). Large results are split between a plain int64 DMA and a packed transfer (16-bit deltas / one byte
+    per edge entry) that host threads widen into the final tensors while the copies run (csrc/ugs_hostio.cu,
+    csrc/ugs_hostdeliver.cpp); UGS_B200_PACKED_D2H=0 forces the plain copy, UGS_B200_DMA_FRACTION the split."""
     import ctypes
     from ugs_b200 import _lib
     from ugs_b200.engine import _ptr, _stream
     nodes, eidx, eptr, sptr, esrc = outs
     nbytes = 8 * (nodes.numel() + eidx.numel() + esrc.numel())
     _to_host_batch.last_d2h_bytes = nbytes + 8 * (eptr.numel() + sptr.numel())  # what crossed PCIe for this call
+    _to_host_batch.last_delivery = "plain int64 copy"
     if nbytes < _PACKED_MIN_BYTES or os.environ.get("UGS_B200_PACKED_D2H", "1") == "0":
         return _to_host(outs)
     L = _lib.lib()
     B, kk, total = int(nodes.shape[0]), int(nodes.shape[1]), int(esrc.numel())
     pairs = 1 if (mode == "sample" and int(k) <= 16) else 0
     dev = nodes.device
+    threads = _host_threads()
+    frac = _dma_fraction(threads)
     with torch.cuda.device(dev):
-        wb = int(L.ugs_wire_bytes(B, kk, total, pairs, 0))  # the int32 layout is large enough for both formats
+        wb = int(L.ugs_deliver_wire_bytes(B, kk, total, pairs)) if frac < 1.0 else 256  # nothing is packed at 1.0
         d_wire = torch.empty(wb, dtype=torch.uint8, device=dev)
         h_wire = torch.empty(wb, dtype=torch.uint8, pin_memory=True)
         h_nodes = torch.empty(nodes.shape, dtype=torch.int64, pin_memory=True)
@@ -151,29 +169,26 @@ def _to_host_batch(outs, mode: str, k: int):
         h_eptr = torch.empty(eptr.shape, dtype=torch.int64, pin_memory=True)
         h_sptr = torch.empty(sptr.shape, dtype=torch.int64, pin_memory=True)
         eidx_c = eidx.contiguous()
-        # node ids / source columns as 16-bit deltas per 4096-element block; int32 if some block spreads too far
-        delta16 = 1
-        _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx_c), _ptr(esrc), total, pairs, delta16,
-                                      _ptr(d_wire), _stream()))
-        bad = ctypes.c_int64(0)
-        _lib.check(L.ugs_pack_status(_ptr(d_wire), B, kk, total, pairs, delta16, ctypes.byref(bad), _stream()))
-        if bad.value:
-            delta16 = 0
-            _lib.check(L.ugs_pack_outputs(_ptr(nodes), B, kk, _ptr(eidx_c), _ptr(esrc), total, pairs, delta16,
-                                          _ptr(d_wire), _stream()))
         h_eptr.copy_(eptr, non_blocking=True)
         h_sptr.copy_(sptr, non_blocking=True)
-        rc = L.ugs_fetch_outputs(_ptr(d_wire), ctypes.c_void_p(h_wire.data_ptr()), B, kk, total, pairs, delta16,
-                                 ctypes.c_void_p(h_nodes.data_ptr()), ctypes.c_void_p(h_eidx.data_ptr()),
-                                 ctypes.c_void_p(h_esrc.data_ptr()), _host_threads(), _stream())
+        stats = (ctypes.c_int64 * 4)()
+        rc = L.ugs_deliver_outputs(_ptr(nodes), B, kk, _ptr(eidx_c), _ptr(esrc), total, pairs, frac, _ptr(d_wire),
+                                   ctypes.c_void_p(h_wire.data_ptr()), wb,
+                                   ctypes.c_void_p(h_nodes.data_ptr()), ctypes.c_void_p(h_eidx.data_ptr()),
+                                   ctypes.c_void_p(h_esrc.data_ptr()), threads, stats, _stream())
         torch.cuda.current_stream().synchronize()
-        if rc != 0:  # a value outside the packed ranges (never for valid sampler output): plain copy
+        if rc == -3:  # UGS_ELIMIT: a value outside the packed ranges (never for valid sampler output): plain copy
             return _to_host(outs)
-    _to_host_batch.last_d2h_bytes = int(L.ugs_wire_bytes(B, kk, total, pairs, delta16)) + 8 * (eptr.numel() + sptr.numel())
+        _lib.check(rc)
+    _to_host_batch.last_d2h_bytes = int(stats[0]) + int(stats[1]) + 8 * (eptr.numel() + sptr.numel())
+    _to_host_batch.last_delivery = (f"dma_fraction {frac:.2f}: {int(stats[1])} B as int64 by DMA + {int(stats[0])} B packed "
+                                    f"({'16-bit deltas' if stats[2] else 'int32'} / {'u8 pairs' if pairs else 'int32 pairs'}), "
+                                    f"widened by {threads} host threads")
     return [h_nodes, h_eidx, h_eptr, h_sptr, h_esrc]
 
 
 _to_host_batch.last_d2h_bytes = 0
+_to_host_batch.last_delivery = None
 
 
 def _want_cuda_out(inp):

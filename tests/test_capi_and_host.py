@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ugs_b200.h but not exported"
     assert set(_lib.EXPORTS) <= set(names)
-    assert L.ugs_abi_version() == 2
+    assert L.ugs_abi_version() == 3
 
 
 def test_workspace_layout_is_host_only_and_consistent():
@@ -167,3 +167,58 @@ def test_ugs_debug_lines_have_the_reference_formats():
     os.environ["UGS_DEBUG"] = "1"
     assert us._debug_on()
     del os.environ["UGS_DEBUG"]
+
+
+def test_host_widening_variants_equal_numpy():
+    """csrc/ugs_hostdeliver.cpp: every widening variant this CPU has (scalar / AVX2 / AVX-512) against numpy, at odd
+    lengths and destination alignments (row 1 of edge_index starts wherever Ebar puts it)."""
+    from ugs_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    ran = set()
+    for isa in (b"scalar", b"avx2", b"avx512"):
+        for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4099):
+            for shift in (0, 1, 3, 5):
+                for kind in (0, 1, 2, 3):
+                    if kind == 0:
+                        src = rng.integers(-2 ** 31, 2 ** 31, size=n, dtype=np.int64).astype(np.int32)
+                        want = src.astype(np.int64)
+                    elif kind in (1, 2):
+                        src = rng.integers(0, 256, size=n, dtype=np.int64).astype(np.uint8)
+                        want = (src & 15).astype(np.int64) if kind == 1 else (src >> 4).astype(np.int64)
+                    else:
+                        src = rng.integers(0, 65536, size=n, dtype=np.int64).astype(np.uint16)
+                        if n:
+                            src[rng.integers(0, n, size=max(1, n // 5))] = 0xFFFF
+                        want = np.where(src == 0xFFFF, -1, 10 ** 12 + src.astype(np.int64))
+                    buf = np.full(n + 16, -7, np.int64)
+                    dst = buf[shift:shift + n]
+                    rc = L.ugs_host_widen(kind, src.ctypes.data if n else None, dst.ctypes.data, n,
+                                          10 ** 12 if kind == 3 else 0, isa)
+                    if rc == -1:
+                        continue
+                    assert rc == 0
+                    ran.add(isa)
+                    assert np.array_equal(dst, want), (isa, n, shift, kind)
+                    assert (buf[:shift] == -7).all() and (buf[shift + n:] == -7).all()
+    assert b"scalar" in ran
+    assert L.ugs_host_isa().decode() in ("scalar", "avx2", "avx512")
+
+
+def test_host_store_bandwidth_probe_and_pool():
+    """The host-side roofline probe runs on the persistent worker pool (no GPU needed) and is re-entrant from threads."""
+    import ctypes
+    import threading
+    from ugs_b200 import _lib
+    L = _lib.lib()
+    buf = np.zeros(1 << 22, np.int64)
+    res = []
+
+    def run():
+        res.append(float(L.ugs_host_store_bandwidth(ctypes.c_void_p(buf.ctypes.data), buf.nbytes, 4, 2)))
+
+    ts = [threading.Thread(target=run) for _ in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(res) == 3 and all(r > 0.1 for r in res)
+    assert (buf == 1).any() or (buf == 0).any()  # written with the probe's pattern (low nibbles of its source block)

@@ -213,29 +213,38 @@ def test_ugs_debug_prints_the_reference_lines(cuda_lib, monkeypatch, capfd):
 
 @pytest.mark.parametrize("mode", ["sample", "graph", "global"])
 def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
-    """CPU outputs travel packed (int32 / one byte per edge entry) and are widened on the host (csrc/ugs_hostio.cu):
-    bit-identical to the plain int64 copy, still pinned, in every mode, for every sampler that returns the 5-tuple."""
+    """CPU outputs are split between a plain int64 DMA and a packed transfer (16-bit deltas or int32 / one byte per
+    edge entry) widened on the host (csrc/ugs_hostio.cu, csrc/ugs_hostdeliver.cpp): bit-identical to the plain int64
+    copy, still pinned, in every mode, at every split, for every sampler that returns the 5-tuple."""
     import epsilon_uniform_sampler
     import rwr_sampler
     import ugs_sampler
     from ugs_b200 import synth
     ei, ptr = synth.make_batch("zinc", 3000, seed=2)
     tei, tptr = torch.from_numpy(ei), torch.from_numpy(ptr)
+    monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
     for mod, kw in ((ugs_sampler, {}), (epsilon_uniform_sampler, dict(epsilon=0.5)), (rwr_sampler, {})):
-        monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
-        packed = mod.sample_batch(tei, tptr, 37, 8, mode, 5, **kw)
         monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
         plain = mod.sample_batch(tei, tptr, 37, 8, mode, 5, **kw)
         monkeypatch.delenv("UGS_B200_PACKED_D2H")
-        for a, b in zip(packed, plain):
-            assert a.dtype == torch.int64 and a.is_pinned() and not a.is_cuda
-            assert torch.equal(a, b)
+        for frac in (None, "0", "0.37", "0.999", "1"):  # model default / all packed / mixed / almost all DMA / all DMA
+            if frac is None:
+                monkeypatch.delenv("UGS_B200_DMA_FRACTION", raising=False)
+            else:
+                monkeypatch.setenv("UGS_B200_DMA_FRACTION", frac)
+            packed = mod.sample_batch(tei, tptr, 37, 8, mode, 5, **kw)
+            assert ugs_sampler._to_host_batch.last_delivery.startswith("dma_fraction")
+            for a, b in zip(packed, plain):
+                assert a.dtype == torch.int64 and a.is_pinned() and not a.is_cuda
+                assert torch.equal(a, b), (mod.__name__, frac)
+        monkeypatch.delenv("UGS_B200_DMA_FRACTION", raising=False)
     # one graph with 120k columns: source columns of neighbouring entries are far apart -> the 16-bit frame-of-reference
     # packing overflows and the int32 wire format takes over
     from ugs_b200 import synth as _synth
     bei, bptr = _synth.barabasi_albert(20000, 3, 7)
+    monkeypatch.setenv("UGS_B200_DMA_FRACTION", "0.25")
     a = ugs_sampler.sample_batch(torch.from_numpy(bei), torch.from_numpy(bptr), 3000, 5, mode, 2)
-    assert ugs_sampler._to_host_batch.last_d2h_bytes > 4 * a[4].numel()  # int32 source columns, not 16-bit deltas
+    assert "(int32 /" in ugs_sampler._to_host_batch.last_delivery  # int32 source columns, not 16-bit deltas
     monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
     b = ugs_sampler.sample_batch(torch.from_numpy(bei), torch.from_numpy(bptr), 3000, 5, mode, 2)
     monkeypatch.delenv("UGS_B200_PACKED_D2H")
