@@ -14,21 +14,13 @@
 //   label_{t+1}(v) = hex(blake2b_16(label_t(v) + "".join(sorted(label_t(u) for u in N(v)))))
 //   after every iteration the sorted (label, count) pairs are appended to a list; the hash is
 //   hex(blake2b_16(str(tuple(list)))), Python's tuple repr: "(('ab..', 2), ('cd..', 1))", "(x,)" for one element.
-// One thread per sample (k <= 16): BLAKE2b's 12 rounds are fully unrolled so the message words stay in registers;
-// labels live in local memory as byte strings; the final tuple string is hashed as it is produced (128-byte blocks).
+// One thread per sample (k <= 16): BLAKE2b's 12 rounds are fully unrolled with message block and state in registers;
+// labels live in shared memory as 16-byte digests (not strings); the final tuple string is hashed as it is produced.
 #include "ugs_common.cuh"
 
 #define WL_MAX_K 16
-#define WL_LAB 32  // a label is at most 32 bytes (hex of a 16-byte digest)
 
 __device__ __forceinline__ u64 rotr64(u64 x, int r) { return (x >> r) | (x << (64 - r)); }
-
-struct B2b {
-    u64 h[8];
-    u64 t;
-    int n;
-    __align__(8) unsigned char buf[128];
-};
 
 #define B2B_G(a, b, c, d, x, y)                   \
     do {                                           \
@@ -42,89 +34,74 @@ struct B2b {
         v[b] = rotr64(v[b] ^ v[c], 63);            \
     } while (0)
 
-#define B2B_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
-    do {                                                                                \
-        B2B_G(0, 4, 8, 12, m[s0], m[s1]);                                               \
-        B2B_G(1, 5, 9, 13, m[s2], m[s3]);                                               \
-        B2B_G(2, 6, 10, 14, m[s4], m[s5]);                                              \
-        B2B_G(3, 7, 11, 15, m[s6], m[s7]);                                              \
-        B2B_G(0, 5, 10, 15, m[s8], m[s9]);                                              \
-        B2B_G(1, 6, 11, 12, m[s10], m[s11]);                                            \
-        B2B_G(2, 7, 8, 13, m[s12], m[s13]);                                             \
-        B2B_G(3, 4, 9, 14, m[s14], m[s15]);                                             \
-    } while (0)
+__constant__ unsigned char b2b_sigma[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
 
-__device__ __noinline__ void b2b_compress(B2b& S, bool last) {
+#define WLT 128  // threads per CTA of the WL kernel; every per-thread array in shared memory is [entries][WLT]
+
+// BLAKE2b compression. The 16 message words of the thread sit in shared memory (column `mcol`, stride WLT: conflict
+// free) and are fetched in the round's permuted order, so the twelve rounds are ONE loop body of eight G functions:
+// the fully unrolled form (48 KB of code per call site) thrashes the instruction cache and ran 2x slower.
+// t = message bytes hashed so far including this block; last = final block; words [nwords, 16) of the block are
+// zeroed here first (padding of the last block).
+__device__ __noinline__ void b2b_compress(u64* h, u64* mcol, int nwords, u64 t, bool last) {
+    for (int i = nwords; i < 16; ++i) mcol[i * WLT] = 0ull;
     const u64 IV0 = 0x6a09e667f3bcc908ull, IV1 = 0xbb67ae8584caa73bull, IV2 = 0x3c6ef372fe94f82bull,
               IV3 = 0xa54ff53a5f1d36f1ull, IV4 = 0x510e527fade682d1ull, IV5 = 0x9b05688c2b3e6c1full,
               IV6 = 0x1f83d9abfb41bd6bull, IV7 = 0x5be0cd19137e2179ull;
-    u64 m[16], v[16];
-    const u64* b = reinterpret_cast<const u64*>(S.buf);
+    u64 v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = b[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = S.h[i];
+    for (int i = 0; i < 8; ++i) v[i] = h[i];
     v[8] = IV0; v[9] = IV1; v[10] = IV2; v[11] = IV3;
-    v[12] = IV4 ^ S.t; v[13] = IV5; v[14] = last ? ~IV6 : IV6; v[15] = IV7;
-    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
-    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
-    B2B_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
-    B2B_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
-    B2B_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
-    B2B_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
-    B2B_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
-    B2B_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
-    B2B_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
-    B2B_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
-    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
-    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    v[12] = IV4 ^ t; v[13] = IV5; v[14] = last ? ~IV6 : IV6; v[15] = IV7;
+#define B2B_M(i) mcol[(int)sg[i] * WLT]
+#pragma unroll 1
+    for (int r = 0; r < 12; ++r) {
+        const unsigned char* sg = b2b_sigma[r];
+        B2B_G(0, 4, 8, 12, B2B_M(0), B2B_M(1));
+        B2B_G(1, 5, 9, 13, B2B_M(2), B2B_M(3));
+        B2B_G(2, 6, 10, 14, B2B_M(4), B2B_M(5));
+        B2B_G(3, 7, 11, 15, B2B_M(6), B2B_M(7));
+        B2B_G(0, 5, 10, 15, B2B_M(8), B2B_M(9));
+        B2B_G(1, 6, 11, 12, B2B_M(10), B2B_M(11));
+        B2B_G(2, 7, 8, 13, B2B_M(12), B2B_M(13));
+        B2B_G(3, 4, 9, 14, B2B_M(14), B2B_M(15));
+    }
+#undef B2B_M
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S.h[i] ^= v[i] ^ v[i + 8];
+    for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[i + 8];
 }
 
-__device__ __forceinline__ void b2b_init(B2b& S) {  // digest_size = 16, no key, fanout = depth = 1
-    S.h[0] = 0x6a09e667f3bcc908ull ^ 0x01010000ull ^ 16ull;
-    S.h[1] = 0xbb67ae8584caa73bull; S.h[2] = 0x3c6ef372fe94f82bull; S.h[3] = 0xa54ff53a5f1d36f1ull;
-    S.h[4] = 0x510e527fade682d1ull; S.h[5] = 0x9b05688c2b3e6c1full; S.h[6] = 0x1f83d9abfb41bd6bull;
-    S.h[7] = 0x5be0cd19137e2179ull;
-    S.t = 0; S.n = 0;
+__device__ __forceinline__ void b2b_init(u64* h) {  // digest_size = 16, no key, fanout = depth = 1
+    h[0] = 0x6a09e667f3bcc908ull ^ 0x01010000ull ^ 16ull;
+    h[1] = 0xbb67ae8584caa73bull; h[2] = 0x3c6ef372fe94f82bull; h[3] = 0xa54ff53a5f1d36f1ull;
+    h[4] = 0x510e527fade682d1ull; h[5] = 0x9b05688c2b3e6c1full; h[6] = 0x1f83d9abfb41bd6bull;
+    h[7] = 0x5be0cd19137e2179ull;
 }
-__device__ __forceinline__ void b2b_put(B2b& S, unsigned char c) {
-    if (S.n == 128) { S.t += 128; b2b_compress(S, false); S.n = 0; }  // a full block is only compressed when more follows
-    S.buf[S.n++] = c;
+
+__device__ __forceinline__ u64 bswap64(u64 x) {
+    return ((u64)__byte_perm((u32)x, 0, 0x0123) << 32) | (u64)__byte_perm((u32)(x >> 32), 0, 0x0123);
 }
-__device__ __forceinline__ void b2b_put_str(B2b& S, const unsigned char* p, int len) {
-    for (int i = 0; i < len; ++i) b2b_put(S, p[i]);
+
+// Eight hex characters (one little-endian message word, first character in the low byte) of four digest bytes given
+// big-endian in w (first byte in the top bits): what hexdigest() prints for them.
+__device__ __forceinline__ u64 hex8(u32 w) {
+    const u32 hi = (w >> 4) & 0x0F0F0F0Fu, lo = w & 0x0F0F0F0Fu;
+    u32 a = __byte_perm(hi, lo, 0x6273);  // characters 0..3: byte0 hi, byte0 lo, byte1 hi, byte1 lo
+    u32 b = __byte_perm(hi, lo, 0x4051);  // characters 4..7: byte2 hi, byte2 lo, byte3 hi, byte3 lo
+    a = a + 0x30303030u + (((a + 0x06060606u) >> 4) & 0x01010101u) * 0x27u;  // 0-9 -> '0'..'9', 10-15 -> 'a'..'f'
+    b = b + 0x30303030u + (((b + 0x06060606u) >> 4) & 0x01010101u) * 0x27u;
+    return ((u64)b << 32) | (u64)a;
 }
-__device__ __forceinline__ void b2b_final(B2b& S, u64& d0, u64& d1) {
-    S.t += (u64)S.n;
-    for (int i = S.n; i < 128; ++i) S.buf[i] = 0;
-    b2b_compress(S, true);
-    d0 = S.h[0]; d1 = S.h[1];
-}
-__device__ __forceinline__ void hex16(u64 d0, u64 d1, unsigned char* out) {  // hexdigest(): bytes in memory order
-    const char* hx = "0123456789abcdef";
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const unsigned b0 = (unsigned)(d0 >> (8 * i)) & 0xFFu, b1 = (unsigned)(d1 >> (8 * i)) & 0xFFu;
-        out[2 * i] = hx[b0 >> 4]; out[2 * i + 1] = hx[b0 & 15];
-        out[16 + 2 * i] = hx[b1 >> 4]; out[16 + 2 * i + 1] = hx[b1 & 15];
-    }
-}
-__device__ __forceinline__ int put_dec(unsigned char* out, unsigned v) {  // str(int) for v < 1000
-    int n = 0;
-    if (v >= 100) out[n++] = (unsigned char)('0' + v / 100);
-    if (v >= 10) out[n++] = (unsigned char)('0' + (v / 10) % 10);
-    out[n++] = (unsigned char)('0' + v % 10);
-    return n;
-}
-// Python str comparison: lexicographic by byte, a proper prefix is smaller
-__device__ __forceinline__ int lab_cmp(const unsigned char* a, int la, const unsigned char* b, int lb) {
-    const int n = la < lb ? la : lb;
-    for (int i = 0; i < n; ++i)
-        if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
-    return la == lb ? 0 : (la < lb ? -1 : 1);
-}
+
+// lexicographic order of two labels held as big-endian keys (equal to Python's str comparison of the hex / decimal
+// strings: zero padding sorts a proper prefix first)
+__device__ __forceinline__ bool key_lt(u64 a0, u64 a1, u64 b0, u64 b1) { return a0 < b0 || (a0 == b0 && a1 < b1); }
 
 // ---- MD5 of every feature row: the node attribute when use_node_features = True (wl_vocab.py:45-49:
 //      hashlib.md5(node_features[i].numpy().tobytes()).hexdigest()[:8] -> the first four digest bytes) ------------------
@@ -186,12 +163,26 @@ k_md5_rows(const unsigned char* __restrict__ x, i64 n_rows, i64 row_bytes, u32* 
     attr32[v] = h[0];
 }
 
-__global__ void __launch_bounds__(128)
+// One thread per sample. Labels are kept as 16-byte digests (two big-endian u64 keys per node, in shared memory, one
+// column per thread), never as strings: the 32 hex characters a label contributes to a message are produced four message
+// words at a time when the block is assembled, neighbour labels are sorted by comparing keys, and the tuple string of the
+// final hash is streamed through an 8-byte shift queue into its own 128-byte block. First-iteration labels (decimal
+// degree or eight hex characters of a feature hash) are at most 8 characters: key word 0 holds them big-endian and zero
+// padded, key word 1 their length.
+// Shared memory per CTA: labels [2 buffers][2 words][k][WLT] + node message block [16][WLT] + stream block [16][WLT]
+// (keeping the stream block in local memory instead -- 48 KB, 4 CTAs/SM -- measured slower: 80 vs 71 ms).
+__global__ void __launch_bounds__(WLT)
 k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ ei_u, const i64* __restrict__ ei_v,
           const i64* __restrict__ edge_ptr, int iterations, const u32* __restrict__ attr32, i64 n_attr,
           u64* __restrict__ digest_out, i32* __restrict__ num_nodes_out) {
+    extern __shared__ u64 wl_sm[];
+    const int tid = threadIdx.x;
+    u64* labs = wl_sm;                               // ((buf * 2 + word) * k + node) * WLT + tid
+    u64* mbuf = wl_sm + (size_t)4 * k * WLT + tid;   // node message block: word i at mbuf[i * WLT]
+    u64* fbuf = mbuf + 16 * WLT;                     // stream block of the final hash
+#define WL_LAB_AT(buf, word, node) labs[(size_t)((((buf) * 2 + (word)) * k) + (node)) * WLT + tid]
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < B; s += stride) {
+    for (i64 s = (i64)blockIdx.x * blockDim.x + tid; s < B; s += stride) {
         int nn = 0;
         for (int j = 0; j < k; ++j) nn += (nodes[s * k + j] >= 0) ? 1 : 0;  // wl_vocab.py:92-93
         num_nodes_out[s] = nn;
@@ -203,88 +194,143 @@ k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ e
             const int u = (int)ei_u[e], v = (int)ei_v[e];
             if (u >= 0 && u < WL_MAX_K && v >= 0 && v < WL_MAX_K) { adj[u] |= 1u << v; adj[v] |= 1u << u; }
         }
-        unsigned char lab[2][WL_MAX_K][WL_LAB];
-        unsigned char len[2][WL_MAX_K];
+        const u32 nmask = (nn >= 32) ? ~0u : ((1u << nn) - 1u);
+        // ---- first labels ------------------------------------------------------------------------------------------
         if (attr32) {  // attr = md5(feature row of the v-th VALID node).hexdigest()[:8]   (wl_vocab.py:45-49,99-103)
             int v = 0;
             for (int j = 0; j < k && v < nn; ++j) {
                 const i64 id = nodes[s * k + j];
                 if (id < 0) continue;
-                const u32 a = (id < n_attr) ? attr32[id] : 0u;
-                const char* hx = "0123456789abcdef";
-                for (int b = 0; b < 4; ++b) {
-                    const unsigned byte = (a >> (8 * b)) & 0xFFu;
-                    lab[0][v][2 * b] = hx[byte >> 4]; lab[0][v][2 * b + 1] = hx[byte & 15];
-                }
-                len[0][v] = 8;
+                const u32 a = (id < n_attr) ? attr32[id] : 0u;   // digest bytes 0..3, byte 0 in the low bits
+                WL_LAB_AT(0, 0, v) = bswap64(hex8(__byte_perm(a, 0, 0x0123)));  // characters big-endian
+                WL_LAB_AT(0, 1, v) = 8;
                 ++v;
             }
         } else {
             for (int v = 0; v < nn; ++v) {  // attr = str(G.degree(v)); a self loop counts twice
                 const unsigned deg = (unsigned)__popc(adj[v] & ~(1u << v)) + (((adj[v] >> v) & 1u) ? 2u : 0u);
-                len[0][v] = (unsigned char)put_dec(lab[0][v], deg);
+                u64 key; int len;
+                if (deg >= 10) { key = ((u64)('0' + deg / 10) << 56) | ((u64)('0' + deg % 10) << 48); len = 2; }
+                else { key = (u64)('0' + deg) << 56; len = 1; }
+                WL_LAB_AT(0, 0, v) = key;
+                WL_LAB_AT(0, 1, v) = (u64)len;
             }
         }
-        B2b F;  // the hash of str(tuple(subgraph_hash_counts)), fed as the string is produced
-        b2b_init(F);
-        b2b_put(F, '(');
+        // ---- the final hash, hash(str(tuple(counts))), fed as the string is produced ---------------------------------
+        u64 fh[8];
+        b2b_init(fh);
+        u64 f_acc = 0, f_blocks = 0;  // shift queue; full blocks already compressed
+        int f_nacc = 0, f_wi = 0;     // bytes in the queue; words in the current block
+        auto f_put = [&](u64 bytes, int len) {  // 1 <= len <= 8 characters, first character in the low byte
+            f_acc |= bytes << (8 * f_nacc);
+            f_nacc += len;
+            if (f_nacc >= 8) {
+                if (f_wi == 16) {  // a full block is only compressed when more data follows
+                    ++f_blocks;
+                    b2b_compress(fh, fbuf, 16, f_blocks * 128ull, false);
+                    f_wi = 0;
+                }
+                fbuf[f_wi * WLT] = f_acc;
+                ++f_wi;
+                f_nacc -= 8;
+                f_acc = f_nacc ? (bytes >> (8 * (len - f_nacc))) : 0ull;
+            }
+        };
+        f_put('(', 1);
         int entries = 0;
         int cur = 0;
         for (int it = 0; it < iterations; ++it) {
             const int nxt = cur ^ 1;
             for (int v = 0; v < nn; ++v) {
-                // neighbours of v sorted by label (insertion sort of indices)
-                int ord[WL_MAX_K];
-                int cnt = 0;
-                u32 mnb = adj[v] & ((nn >= 32) ? ~0u : ((1u << nn) - 1u));
-                while (mnb) {
-                    const int u = __ffs(mnb) - 1;
-                    mnb &= mnb - 1;
-                    int p = cnt++;
-                    while (p > 0 && lab_cmp(lab[cur][ord[p - 1]], len[cur][ord[p - 1]], lab[cur][u], len[cur][u]) > 0) {
-                        ord[p] = ord[p - 1];
-                        --p;
+                u32 rem = adj[v] & nmask;
+                const int pieces = __popc(rem) + 1;  // own label, then the neighbours' labels in sorted order
+                u64 h[8];
+                b2b_init(h);
+                u64 acc = 0, total = 0, blocks = 0;
+                int nacc = 0, wi = 0;
+                for (int p = 0; p < pieces; ++p) {
+                    u64 a0, a1;
+                    if (p == 0) { a0 = WL_LAB_AT(cur, 0, v); a1 = WL_LAB_AT(cur, 1, v); }
+                    else {  // the smallest remaining neighbour label
+                        int best = -1;
+                        a0 = 0; a1 = 0;
+                        for (u32 r = rem; r; r &= r - 1) {
+                            const int u = __ffs(r) - 1;
+                            const u64 k0 = WL_LAB_AT(cur, 0, u), k1 = WL_LAB_AT(cur, 1, u);
+                            if (best < 0 || key_lt(k0, k1, a0, a1)) { best = u; a0 = k0; a1 = k1; }
+                        }
+                        rem &= ~(1u << best);
                     }
-                    ord[p] = u;
+                    if (it > 0) {  // 32 hex characters: four whole message words
+                        if (wi == 16) { ++blocks; b2b_compress(h, mbuf, 16, blocks * 128ull, false); wi = 0; }
+                        mbuf[wi * WLT] = hex8((u32)(a0 >> 32)); mbuf[(wi + 1) * WLT] = hex8((u32)a0);
+                        mbuf[(wi + 2) * WLT] = hex8((u32)(a1 >> 32)); mbuf[(wi + 3) * WLT] = hex8((u32)a1);
+                        wi += 4;
+                        total += 32;
+                    } else {       // at most 8 characters, byte granular: through the shift queue
+                        const int len = (int)a1;
+                        const u64 bytes = bswap64(a0);  // first character in the low byte
+                        total += (u64)len;
+                        acc |= bytes << (8 * nacc);
+                        nacc += len;
+                        if (nacc >= 8) {
+                            if (wi == 16) { ++blocks; b2b_compress(h, mbuf, 16, blocks * 128ull, false); wi = 0; }
+                            mbuf[wi * WLT] = acc;
+                            ++wi;
+                            nacc -= 8;
+                            acc = nacc ? (bytes >> (8 * (len - nacc))) : 0ull;
+                        }
+                    }
                 }
-                B2b H;
-                b2b_init(H);
-                b2b_put_str(H, lab[cur][v], len[cur][v]);
-                for (int q = 0; q < cnt; ++q) b2b_put_str(H, lab[cur][ord[q]], len[cur][ord[q]]);
-                u64 d0, d1;
-                b2b_final(H, d0, d1);
-                hex16(d0, d1, lab[nxt][v]);
-                len[nxt][v] = 32;
+                if (nacc) {
+                    if (wi == 16) { ++blocks; b2b_compress(h, mbuf, 16, blocks * 128ull, false); wi = 0; }
+                    mbuf[wi * WLT] = acc;
+                    ++wi;
+                }
+                b2b_compress(h, mbuf, wi, total, true);
+                WL_LAB_AT(nxt, 0, v) = bswap64(h[0]);  // big-endian keys: hex-string order == numeric order
+                WL_LAB_AT(nxt, 1, v) = bswap64(h[1]);
             }
-            // Counter(node_labels.values()) sorted by label
-            int ord[WL_MAX_K];
-            for (int v = 0; v < nn; ++v) {
-                int p = v;
-                while (p > 0 && lab_cmp(lab[nxt][ord[p - 1]], 32, lab[nxt][v], 32) > 0) { ord[p] = ord[p - 1]; --p; }
-                ord[p] = v;
-            }
-            for (int a = 0; a < nn;) {
-                int b = a + 1;
-                while (b < nn && lab_cmp(lab[nxt][ord[a]], 32, lab[nxt][ord[b]], 32) == 0) ++b;
-                if (entries++) { b2b_put(F, ','); b2b_put(F, ' '); }
-                b2b_put(F, '('); b2b_put(F, '\'');
-                b2b_put_str(F, lab[nxt][ord[a]], 32);
-                b2b_put(F, '\''); b2b_put(F, ','); b2b_put(F, ' ');
-                unsigned char dec[4];
-                const int dl = put_dec(dec, (unsigned)(b - a));
-                b2b_put_str(F, dec, dl);
-                b2b_put(F, ')');
-                a = b;
+            // ---- Counter(node_labels.values()), sorted by label: repeatedly the smallest label above the previous one
+            u64 p0 = 0, p1 = 0;
+            bool have_prev = false;
+            for (int done = 0; done < nn;) {
+                u64 b0 = 0, b1 = 0;
+                int c = 0;
+                for (int v = 0; v < nn; ++v) {
+                    const u64 k0 = WL_LAB_AT(nxt, 0, v), k1 = WL_LAB_AT(nxt, 1, v);
+                    if (have_prev && !key_lt(p0, p1, k0, k1)) continue;
+                    if (c == 0 || key_lt(k0, k1, b0, b1)) { b0 = k0; b1 = k1; c = 1; }
+                    else if (k0 == b0 && k1 == b1) ++c;
+                }
+                if (entries++) f_put((u64)',' | ((u64)' ' << 8), 2);
+                f_put((u64)'(' | ((u64)'\'' << 8), 2);
+                f_put(hex8((u32)(b0 >> 32)), 8); f_put(hex8((u32)b0), 8);
+                f_put(hex8((u32)(b1 >> 32)), 8); f_put(hex8((u32)b1), 8);
+                f_put((u64)'\'' | ((u64)',' << 8) | ((u64)' ' << 16), 3);
+                if (c >= 10) f_put((u64)('0' + c / 10) | ((u64)('0' + c % 10) << 8), 2);
+                else f_put((u64)('0' + c), 1);
+                f_put(')', 1);
+                p0 = b0; p1 = b1; have_prev = true;
+                done += c;
             }
             cur = nxt;
         }
-        if (entries == 1) b2b_put(F, ',');
-        b2b_put(F, ')');
-        u64 d0, d1;
-        b2b_final(F, d0, d1);
-        digest_out[2 * s] = d0;
-        digest_out[2 * s + 1] = d1;
+        if (entries == 1) f_put(',', 1);
+        f_put(')', 1);
+        {
+            const u64 total = f_blocks * 128ull + (u64)f_wi * 8ull + (u64)f_nacc;
+            if (f_nacc) {
+                if (f_wi == 16) { ++f_blocks; b2b_compress(fh, fbuf, 16, f_blocks * 128ull, false); f_wi = 0; }
+                fbuf[f_wi * WLT] = f_acc;
+                ++f_wi;
+            }
+            b2b_compress(fh, fbuf, f_wi, total, true);
+        }
+        digest_out[2 * s] = fh[0];
+        digest_out[2 * s + 1] = fh[1];
     }
+#undef WL_LAB_AT
 }
 
 // ids[s] = vocabulary id of digest s (binary search over the vocabulary's digests sorted as (bswap d0, bswap d1),
@@ -333,10 +379,12 @@ extern "C" int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t blocks = (B + 127) / 128;
+    int64_t blocks = (B + WLT - 1) / WLT;
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
-    k_wl_hash<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(nodes, B, k, edge_index_s, edge_index_s + total, edge_ptr,
+    const size_t smem = sizeof(u64) * WLT * (size_t)(4 * k + 32);  // k = 8: 64 KB, k = 16: 96 KB
+    UGS_CUDA_CHECK(cudaFuncSetAttribute(k_wl_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wl_hash<<<(unsigned)blocks, WLT, smem, (cudaStream_t)stream_>>>(nodes, B, k, edge_index_s, edge_index_s + total, edge_ptr,
                                                                   iterations, node_attr32, n_attr, (u64*)digest_out,
                                                                   num_nodes_out);
     UGS_LAUNCH_CHECK("k_wl_hash");
