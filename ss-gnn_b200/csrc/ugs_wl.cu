@@ -34,7 +34,7 @@ __device__ __forceinline__ u64 rotr64(u64 x, int r) { return (x >> r) | (x << (6
         v[b] = rotr64(v[b] ^ v[c], 63);            \
     } while (0)
 
-__constant__ unsigned char b2b_sigma[12][16] = {
+__constant__ __align__(16) unsigned char b2b_sigma[12][16] = {
     {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
     {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
     {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
@@ -59,19 +59,28 @@ __device__ __noinline__ void b2b_compress(u64* h, u64* mcol, int nwords, u64 t, 
     for (int i = 0; i < 8; ++i) v[i] = h[i];
     v[8] = IV0; v[9] = IV1; v[10] = IV2; v[11] = IV3;
     v[12] = IV4 ^ t; v[13] = IV5; v[14] = last ? ~IV6 : IV6; v[15] = IV7;
-#define B2B_M(i) mcol[(int)sg[i] * WLT]
+    // One loop body for the twelve rounds (the fully unrolled form, 48 KB of code, is slower: 82 vs 69 ms -- instruction
+    // cache). The round's permutation comes as one 16-byte constant load and its sixteen message words are fetched from
+    // shared memory together, before the eight G functions, so that their latency overlaps.
 #pragma unroll 1
     for (int r = 0; r < 12; ++r) {
-        const unsigned char* sg = b2b_sigma[r];
-        B2B_G(0, 4, 8, 12, B2B_M(0), B2B_M(1));
-        B2B_G(1, 5, 9, 13, B2B_M(2), B2B_M(3));
-        B2B_G(2, 6, 10, 14, B2B_M(4), B2B_M(5));
-        B2B_G(3, 7, 11, 15, B2B_M(6), B2B_M(7));
-        B2B_G(0, 5, 10, 15, B2B_M(8), B2B_M(9));
-        B2B_G(1, 6, 11, 12, B2B_M(10), B2B_M(11));
-        B2B_G(2, 7, 8, 13, B2B_M(12), B2B_M(13));
-        B2B_G(3, 4, 9, 14, B2B_M(14), B2B_M(15));
+        const uint4 sg = reinterpret_cast<const uint4*>(b2b_sigma)[r];
+        u64 mw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const u32 w = (i < 4) ? sg.x : (i < 8) ? sg.y : (i < 12) ? sg.z : sg.w;
+            mw[i] = mcol[((w >> (8 * (i & 3))) & 0xFFu) * WLT];
+        }
+        B2B_G(0, 4, 8, 12, mw[0], mw[1]);
+        B2B_G(1, 5, 9, 13, mw[2], mw[3]);
+        B2B_G(2, 6, 10, 14, mw[4], mw[5]);
+        B2B_G(3, 7, 11, 15, mw[6], mw[7]);
+        B2B_G(0, 5, 10, 15, mw[8], mw[9]);
+        B2B_G(1, 6, 11, 12, mw[10], mw[11]);
+        B2B_G(2, 7, 8, 13, mw[12], mw[13]);
+        B2B_G(3, 4, 9, 14, mw[14], mw[15]);
     }
+#define B2B_M(i) 0
 #undef B2B_M
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[i + 8];
@@ -169,8 +178,7 @@ k_md5_rows(const unsigned char* __restrict__ x, i64 n_rows, i64 row_bytes, u32* 
 // final hash is streamed through an 8-byte shift queue into its own 128-byte block. First-iteration labels (decimal
 // degree or eight hex characters of a feature hash) are at most 8 characters: key word 0 holds them big-endian and zero
 // padded, key word 1 their length.
-// Shared memory per CTA: labels [2 buffers][2 words][k][WLT] + node message block [16][WLT] + stream block [16][WLT]
-// (keeping the stream block in local memory instead -- 48 KB, 4 CTAs/SM -- measured slower: 80 vs 71 ms).
+// Shared memory per CTA: labels [2 buffers][2 words][k][WLT] + the message block being compressed [16][WLT].
 __global__ void __launch_bounds__(WLT)
 k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ ei_u, const i64* __restrict__ ei_v,
           const i64* __restrict__ edge_ptr, int iterations, const u32* __restrict__ attr32, i64 n_attr,
@@ -178,8 +186,7 @@ k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ e
     extern __shared__ u64 wl_sm[];
     const int tid = threadIdx.x;
     u64* labs = wl_sm;                               // ((buf * 2 + word) * k + node) * WLT + tid
-    u64* mbuf = wl_sm + (size_t)4 * k * WLT + tid;   // node message block: word i at mbuf[i * WLT]
-    u64* fbuf = mbuf + 16 * WLT;                     // stream block of the final hash
+    u64* mbuf = wl_sm + (size_t)4 * k * WLT + tid;   // message block being compressed: word i at mbuf[i * WLT]
 #define WL_LAB_AT(buf, word, node) labs[(size_t)((((buf) * 2 + (word)) * k) + (node)) * WLT + tid]
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 s = (i64)blockIdx.x * blockDim.x + tid; s < B; s += stride) {
@@ -219,22 +226,34 @@ k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ e
         // ---- the final hash, hash(str(tuple(counts))), fed as the string is produced ---------------------------------
         u64 fh[8];
         b2b_init(fh);
+        // The string is queued as 8-byte words in a per-thread buffer and its complete 128-byte blocks are compressed
+        // after every iteration, in a loop all lanes of the warp walk together. (Compressing inside f_put, whenever a
+        // lane's block fills up, happens at a different moment in every lane: the 3000-instruction compression then runs
+        // once per lane instead of once per warp.) One iteration appends at most 16 entries of 42 characters.
+        u64 fs[WL_MAX_K * 6 + 20];
         u64 f_acc = 0, f_blocks = 0;  // shift queue; full blocks already compressed
-        int f_nacc = 0, f_wi = 0;     // bytes in the queue; words in the current block
+        int f_nacc = 0, f_wi = 0;     // bytes in the queue; words in fs[]
         auto f_put = [&](u64 bytes, int len) {  // 1 <= len <= 8 characters, first character in the low byte
             f_acc |= bytes << (8 * f_nacc);
             f_nacc += len;
             if (f_nacc >= 8) {
-                if (f_wi == 16) {  // a full block is only compressed when more data follows
-                    ++f_blocks;
-                    b2b_compress(fh, fbuf, 16, f_blocks * 128ull, false);
-                    f_wi = 0;
-                }
-                fbuf[f_wi * WLT] = f_acc;
-                ++f_wi;
+                fs[f_wi++] = f_acc;
                 f_nacc -= 8;
                 f_acc = f_nacc ? (bytes >> (8 * (len - f_nacc))) : 0ull;
             }
+        };
+        // compress the complete blocks in fs[] (all of them: more data follows) and move the tail to the front
+        auto f_drain = [&]() {
+            const int nfull = f_wi >> 4;
+            for (int b = 0; b < nfull; ++b) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mbuf[i * WLT] = fs[16 * b + i];
+                ++f_blocks;
+                b2b_compress(fh, mbuf, 16, f_blocks * 128ull, false);
+            }
+            const int tail = f_wi - 16 * nfull;
+            for (int i = 0; i < tail; ++i) fs[i] = fs[16 * nfull + i];
+            f_wi = tail;
         };
         f_put('(', 1);
         int entries = 0;
@@ -314,18 +333,24 @@ k_wl_hash(const i64* __restrict__ nodes, i64 B, int k, const i64* __restrict__ e
                 p0 = b0; p1 = b1; have_prev = true;
                 done += c;
             }
+            f_drain();  // ")" (or ",)") still follows: every complete block can go
             cur = nxt;
         }
         if (entries == 1) f_put(',', 1);
         f_put(')', 1);
         {
             const u64 total = f_blocks * 128ull + (u64)f_wi * 8ull + (u64)f_nacc;
-            if (f_nacc) {
-                if (f_wi == 16) { ++f_blocks; b2b_compress(fh, fbuf, 16, f_blocks * 128ull, false); f_wi = 0; }
-                fbuf[f_wi * WLT] = f_acc;
-                ++f_wi;
+            if (f_nacc) fs[f_wi++] = f_acc;
+            if (f_wi > 16) {  // the two closing characters completed a block and spilled over: that block is not the last
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mbuf[i * WLT] = fs[i];
+                ++f_blocks;
+                b2b_compress(fh, mbuf, 16, f_blocks * 128ull, false);
+                for (int i = 16; i < f_wi; ++i) fs[i - 16] = fs[i];
+                f_wi -= 16;
             }
-            b2b_compress(fh, fbuf, f_wi, total, true);
+            for (int i = 0; i < f_wi; ++i) mbuf[i * WLT] = fs[i];
+            b2b_compress(fh, mbuf, f_wi, total, true);
         }
         digest_out[2 * s] = fh[0];
         digest_out[2 * s + 1] = fh[1];
@@ -382,7 +407,7 @@ extern "C" int ugs_wl_hash(const int64_t* nodes, int64_t B, int k, const int64_t
     int64_t blocks = (B + WLT - 1) / WLT;
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
-    const size_t smem = sizeof(u64) * WLT * (size_t)(4 * k + 32);  // k = 8: 64 KB, k = 16: 96 KB
+    const size_t smem = sizeof(u64) * WLT * (size_t)(4 * k + 16);  // k = 8: 48 KB, k = 16: 80 KB
     UGS_CUDA_CHECK(cudaFuncSetAttribute(k_wl_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_wl_hash<<<(unsigned)blocks, WLT, smem, (cudaStream_t)stream_>>>(nodes, B, k, edge_index_s, edge_index_s + total, edge_ptr,
                                                                   iterations, node_attr32, n_attr, (u64*)digest_out,
