@@ -254,11 +254,14 @@ int ugs_fused_finish(const int64_t* ei_u, const int64_t* ei_v, const int64_t* ei
 /* ---- exact-uniform accept/reject variant (not in the reference, see oracle/uni_oracle.c) ---------
  * ugs_preproc_uniform: call after ugs_preproc_batch. Replaces order / suffix_deg / suf / bucket_b / cum / Z by
  * the degree-dominating-order tables of the uniform mode and writes the acceptance constant C per graph.
- * Bitmask path only: every sampled graph must have <= 64 nodes and k <= 8 (UGS_ELIMIT otherwise).
+ * k <= 8. Bitmask-path graphs (<= 64 nodes) get their tables from a warp each; general-path graphs (up to 4096 nodes;
+ * n_general / max_n_general from ugs_batch_info) from a CTA each, and their samples from one warp per sample whose
+ * p(S|r) comes from a subset-sum transform over the members' adjacency masks (csrc/ugs_uniform_general.cu).
+ * UGS_ELIMIT for k > 8 or a graph above 4096 nodes.
  * Then ugs_sample_batch(variant = UGS_VARIANT_UNIFORM) and ugs_emit_edges as usual. */
 #define UGS_UNIFORM_MAX_TRIALS 4096
-int ugs_preproc_uniform(const int64_t* ptr, int64_t G, int64_t node_base, int k, int64_t n_general, void* workspace,
-                        const ugs_layout* L, void* stream);
+int ugs_preproc_uniform(const int64_t* ptr, int64_t G, int64_t node_base, int k, int64_t n_general,
+                        int64_t max_n_general, void* workspace, const ugs_layout* L, void* stream);
 
 /* ---- epsilon-uniform variant (reference src/samplers/epsilon_uniform_sampler) --------------------
  * Same workspace as the UGS path (ugs_segment_batch + ugs_preproc_batch); only the multigraph CSR is used.

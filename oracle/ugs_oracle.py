@@ -164,28 +164,38 @@ def sample_batch(edge_index, ptr, m_per_graph: int, k: int, mode: str = "sample"
 
 
 class UniformTables:
-    """Tables of the exact-uniform accept/reject mode (oracle/uni_oracle.c) for one graph given its CSR."""
+    """Tables of the exact-uniform accept/reject mode (oracle/uni_oracle.c) for one graph given its CSR: the 64-bit mask
+    statement for n <= 64 (general=False), the adjacency-list statement for any n (general=True, the default above 64)."""
 
-    def __init__(self, edge_index, num_nodes: int, k: int):
+    def __init__(self, edge_index, num_nodes: int, k: int, general=None):
         self._P = Preproc(edge_index, num_nodes, k)
         d = self._P.dump()
         self._indptr, self._indices = d["indptr"], d["indices"]
         L = lib()
-        L.uni_oracle_create.restype = ctypes.c_void_p
-        L.uni_oracle_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-        L.uni_oracle_free.argtypes = [ctypes.c_void_p]
-        L.uni_oracle_dump.argtypes = [ctypes.c_void_p] * 7
-        L.uni_oracle_sample_nodes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
-                                              ctypes.c_void_p, ctypes.c_void_p]
         self.n, self.k = int(num_nodes), int(k)
-        self._h = L.uni_oracle_create(_p(self._indptr), _p(self._indices), self.n, self.k)
+        self.general = (self.n > 64) if general is None else bool(general)
+        vp = ctypes.c_void_p
+        if self.general:
+            L.uni_gen_create.restype = vp
+            L.uni_gen_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+            L.uni_gen_free.argtypes = [vp]
+            L.uni_gen_dump.argtypes = [vp] * 6
+            L.uni_gen_sample_nodes.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+            self._h = L.uni_gen_create(_p(self._indptr), _p(self._indices), self.n, self.k)
+        else:
+            L.uni_oracle_create.restype = vp
+            L.uni_oracle_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+            L.uni_oracle_free.argtypes = [vp]
+            L.uni_oracle_dump.argtypes = [vp] * 7
+            L.uni_oracle_sample_nodes.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+            self._h = L.uni_oracle_create(_p(self._indptr), _p(self._indices), self.n, self.k)
         if not self._h:
-            raise RuntimeError("uniform mode needs n <= 64 and k <= 8")
+            raise RuntimeError("uniform mode needs k <= 8 (and n <= 64 for the mask statement)")
 
     def __del__(self):
         try:
             if self._h:
-                lib().uni_oracle_free(self._h)
+                (lib().uni_gen_free if self.general else lib().uni_oracle_free)(self._h)
                 self._h = None
         except Exception:
             pass
@@ -195,14 +205,19 @@ class UniformTables:
         d = dict(order=np.zeros(n, np.int32), dsuf=np.zeros(n, np.int32), suf=np.zeros(n, np.uint64),
                  b=np.zeros(n, np.float64), cum=np.zeros(n, np.float64))
         zc = np.zeros(2, np.float64)
-        lib().uni_oracle_dump(self._h, _p(d["order"]), _p(d["dsuf"]), _p(d["suf"]), _p(d["b"]), _p(d["cum"]), _p(zc))
+        if self.general:
+            lib().uni_gen_dump(self._h, _p(d["order"]), _p(d["dsuf"]), _p(d["b"]), _p(d["cum"]), _p(zc))
+            del d["suf"]
+        else:
+            lib().uni_oracle_dump(self._h, _p(d["order"]), _p(d["dsuf"]), _p(d["suf"]), _p(d["b"]), _p(d["cum"]), _p(zc))
         d["Z"], d["C"] = float(zc[0]), float(zc[1])
         return d
 
     def sample_nodes(self, m: int, seed: int = 42, graph_index: int = 0):
         out = np.full((m, self.k), -1, np.int32)
         trials = np.zeros(1, np.int64)
-        lib().uni_oracle_sample_nodes(self._h, m, seed & (2 ** 64 - 1), graph_index, _p(out), _p(trials))
+        fn = lib().uni_gen_sample_nodes if self.general else lib().uni_oracle_sample_nodes
+        fn(self._h, m, seed & (2 ** 64 - 1), graph_index, _p(out), _p(trials))
         return out, int(trials[0])
 
 

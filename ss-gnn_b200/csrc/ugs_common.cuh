@@ -128,6 +128,35 @@ __device__ __forceinline__ double root_x(u32 w0, u32 w1, double Z) {
     return ((double)u53 * (1.0 / 9007199254740992.0)) * Z;
 }
 
+// inclusive warp prefix sum of a small non-negative int
+__device__ __forceinline__ int warp_incl_scan(int c, int lane) {
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += y;
+    }
+    return incl;
+}
+
+// First index a in [0, n) with cm[a] > x, or n - 1 when there is none: what the scalar binary search of the bitmask
+// path returns, found with 32 probes per round (a 10^5-entry CDF: 4 dependent rounds of L2 latency instead of 17).
+__device__ __forceinline__ int warp_cdf_search(const double* __restrict__ cm, int n, double x, int lane) {
+    int lo = 0, len = n;
+    while (len > 32) {
+        const int stride = (len + 31) >> 5;
+        const int idx = min(lo + (lane + 1) * stride - 1, lo + len - 1);
+        const u32 ball = __ballot_sync(FULL_MASK, cm[idx] > x);
+        if (ball == 0u) return n - 1;  // the last probe is the last element of the range
+        const int first = __ffs(ball) - 1;
+        const int hi = min(lo + (first + 1) * stride - 1, lo + len - 1);  // probe `first`: true
+        lo += first * stride;                                            // probe `first - 1` (at lo - 1): false
+        len = hi - lo + 1;
+    }
+    const u32 ball = __ballot_sync(FULL_MASK, lane < len && cm[lo + lane] > x);
+    return ball ? lo + __ffs(ball) - 1 : n - 1;
+}
+
 // internal entry points shared between translation units
 int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
                           uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,

@@ -599,7 +599,8 @@ extern "C" int ugs_eps_emit_edges(const int64_t* edge_index, int64_t E, const in
 }
 
 // =====================================================================================================
-// Exact-uniform accept/reject variant (rule stated in oracle/uni_oracle.c). Bitmask path only.
+// Exact-uniform accept/reject variant (rule stated in oracle/uni_oracle.c): bitmask-path graphs here,
+// general-path graphs in ugs_uniform_general.cu.
 // =====================================================================================================
 #define UNI_WARPS 8
 
@@ -888,25 +889,29 @@ k_sample_uniform_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m,
     }
 }
 
+int ugs_launch_uniform_tables_general(const i64* ptr, i64 node_base, int k, i64 n_general, i64 max_n_general, WS& w,
+                                      cudaStream_t st);  // ugs_uniform_general.cu
+int ugs_launch_sample_uniform_general(const i64* ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, i64 n_general,
+                                      WS& w, i64* nodes, i64* edge_ptr, cudaStream_t st);
+
 extern "C" int ugs_preproc_uniform(const int64_t* ptr, int64_t G, int64_t node_base, int k, int64_t n_general,
-                                   void* workspace, const ugs_layout* L, void* stream_) {
+                                   int64_t max_n_general, void* workspace, const ugs_layout* L, void* stream_) {
     if (!workspace || !L) return ugs_set_error(UGS_EINVAL, "NULL workspace/layout");
     if (k < 1 || k > 8) return ugs_set_error(UGS_ELIMIT, "the uniform variant supports k <= 8");
-    if (n_general > 0)
-        return ugs_set_error(UGS_ELIMIT, "the uniform variant supports graphs with <= %d nodes and <= %d edge columns",
-                             UGS_SMALL_MAX_N, UGS_SMALL_MAX_COLS);
     if (G <= 0) return UGS_OK;
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(workspace, L);
-    k_uniform_tables_small<<<(unsigned)((G + UNI_WARPS - 1) / UNI_WARPS), UNI_WARPS * 32, 0, st>>>(ptr, G, node_base, k, w);
-    UGS_LAUNCH_CHECK("k_uniform_tables_small");
-    return UGS_OK;
+    if (n_general < G) {
+        k_uniform_tables_small<<<(unsigned)((G + UNI_WARPS - 1) / UNI_WARPS), UNI_WARPS * 32, 0, st>>>(ptr, G, node_base, k, w);
+        UGS_LAUNCH_CHECK("k_uniform_tables_small");
+    }
+    return ugs_launch_uniform_tables_general(ptr, node_base, k, n_general, max_n_general, w, st);
 }
 
 // called from ugs_sample_batch (ugs_sample.cu) for UGS_VARIANT_UNIFORM
 int ugs_launch_sample_uniform(const i64* ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, i64 n_general,
                               WS& w, i64* nodes, i64* edge_ptr, i64* sample_ptr, cudaStream_t st) {
-    if (k > 8 || n_general > 0) return ugs_set_error(UGS_ELIMIT, "the uniform variant supports k <= 8 and graphs with <= 64 nodes");
+    if (k > 8) return ugs_set_error(UGS_ELIMIT, "the uniform variant supports k <= 8");
     int tpi; int64_t ipg;
     eps_items(m, &tpi, &ipg);
     const int64_t items = G * ipg;
@@ -915,5 +920,6 @@ int ugs_launch_sample_uniform(const i64* ptr, i64 G, i64 node_base, i64 m, int k
     k_sample_uniform_small<<<(unsigned)((items + UNI_WARPS - 1) / UNI_WARPS), UNI_WARPS * 32, smem, st>>>(
         ptr, G, node_base, m, k, seed, gbase, tpi, ipg, w, nodes, edge_ptr, sample_ptr);
     UGS_LAUNCH_CHECK("k_sample_uniform_small");
-    return UGS_OK;
+    // general-path graphs (the kernel above wrote -1 rows for them): one warp per sample, after it on the same stream
+    return ugs_launch_sample_uniform_general(ptr, node_base, m, k, seed, gbase, n_general, w, nodes, edge_ptr, st);
 }

@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_hostdeliver.cpp", "ugs_fused.cu", "ugs_variants.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_hostdeliver.cpp", "ugs_fused.cu", "ugs_variants.cu", "ugs_uniform_general.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(CSRC, "ugs_hostio.h"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
@@ -107,7 +107,7 @@ def lib():
     L.ugs_sort_scratch_bytes.restype = sz
     L.ugs_sort_scratch_bytes.argtypes = [i64]
     L.ugs_sort_columns.argtypes = [i64, i64, vp, LP, vp, sz, vp, vp]
-    L.ugs_preproc_uniform.argtypes = [vp, i64, i64, ci, i64, vp, LP, vp]
+    L.ugs_preproc_uniform.argtypes = [vp, i64, i64, ci, i64, i64, vp, LP, vp]
     L.ugs_eps_sample_batch.argtypes = [vp, i64, i64, i64, ci, u64, u64, ctypes.c_double, i64, vp, LP, vp, sz, vp, vp, vp, vp]
     L.ugs_eps_emit_edges.argtypes = [vp, i64, vp, i64, i64, i64, ci, ci, vp, i64, vp, LP, vp, vp, i64, vp, vp, vp]
     L.ugs_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp]

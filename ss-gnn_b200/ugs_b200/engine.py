@@ -113,7 +113,8 @@ class DeviceBatch:
             self._preproc(self.n_general, self.n_large, 2 if speculative else 3)
             if self.variant == "uniform":  # degree-dominating-order tables of the exact-uniform mode
                 _lib.check(L.ugs_preproc_uniform(_ptr(self.ptr), self.G, self.node_base, self.k, self.n_general,
-                                                 _ptr(self.ws), ctypes.byref(self.layout), _stream()))
+                                                 self.max_n_general, _ptr(self.ws), ctypes.byref(self.layout),
+                                                 _stream()))
 
     def _preproc(self, n_general: int, n_large: int, parts: int):
         _lib.check(_lib.lib().ugs_preproc_batch_parts(_ptr(self.edge_index), self.E, _ptr(self.ptr), self.G,

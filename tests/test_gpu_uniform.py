@@ -71,9 +71,71 @@ def test_uniform_variant_passes_chi_square_against_uniform(cuda_lib, name, und, 
     assert xl.chi_square(cr, law, M)[0] > chi2.ppf(0.999, df)
 
 
+def test_uniform_variant_on_general_path_graphs_bit_exact(cuda_lib):
+    """Graphs above 64 vertices (PROTEINS has them) take the general path: tables (degree-dominating order, suffix
+    degrees, weights, CDF, acceptance constant) and samples bit-exact against the adjacency-list oracle, in one batch
+    with bitmask-path graphs (per-graph dispatch)."""
+    from oracle import ugs_oracle as uo
+    from ugs_b200 import synth
+    ei, ptr = synth.make_batch("proteins", 40, seed=1)
+    assert np.diff(ptr).max() > 64
+    for k, m in ((4, 6), (3, 5), (6, 3)):
+        b = _batch(ei, ptr, k, variant="uniform")
+        assert b.n_general > 0
+        gi = b.ginfo()
+        V = {nm: b.view(nm).cpu().numpy() for nm in ("order", "index_of", "suffix_deg", "bucket_b", "cum", "gaux")}
+        for g in range(len(ptr) - 1):
+            lo, n = int(ptr[g]), int(ptr[g + 1] - ptr[g])
+            if n < k:
+                continue
+            lc, _ = per_graph_columns(ei, ptr, g)
+            d = uo.UniformTables(lc, n, k).dump()
+            assert np.array_equal(V["order"][lo:lo + n], d["order"]), (g, n)
+            assert np.array_equal(V["suffix_deg"][lo:lo + n], d["dsuf"]), (g, n)
+            assert np.array_equal(V["bucket_b"][lo:lo + n], d["b"]) and np.array_equal(V["cum"][lo:lo + n], d["cum"]), (g, n)
+            assert float(gi["Z"][g]) == d["Z"] and (d["Z"] == 0 or float(V["gaux"][g]) == d["C"]), (g, n)
+            if n > 64:
+                assert np.array_equal(V["index_of"][lo:lo + n][d["order"]], np.arange(n))
+        outs, stats = b.sample(m, k, "sample", seed=5)
+        ref = uo.sample_batch_uniform(ei, ptr, m, k, "sample", 5)
+        for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r), (name, k)
+        assert stats["n_trials"] >= stats["n_graphlets"] - stats["n_incomplete"]
+
+
+def test_uniform_variant_chi_square_on_a_100_node_graph(cuda_lib):
+    """PROTEINS-shaped 100-node graph, k = 4 (general path): 400 000 samples against the uniform law over all 3033
+    connected induced 4-subgraphs, alpha = 0.001, CV below the reference scripts' 0.15 (sampling noise alone is
+    1/sqrt(132) = 0.087 at this size) -- and the reference law fails the same test."""
+    from oracle import exact_law as xl, ugs_oracle as uo
+    from test_uniform_oracle import uniform_test_graph
+    ei, ptr = uniform_test_graph()
+    n, k, M = int(ptr[1]), 4, 400000
+    rows = xl.rows_from_dump(uo.Preproc(ei, n, k).dump())
+    adj = [set(r) - {v} for v, r in enumerate(rows)]
+    frontier = {frozenset([v]) for v in range(n)}
+    for _ in range(k - 1):
+        frontier = {s_ | {w} for s_ in frontier for u in s_ for w in adj[u] if w not in s_}
+    law = {s_: 1.0 / len(frontier) for s_ in frontier}
+    b = _batch(ei, ptr, k, variant="uniform")
+    assert b.n_general == 1
+    (nodes, *_), stats = b.sample(M, k, "sample", seed=77)
+    assert stats["n_incomplete"] == 0
+    want, _ = uo.UniformTables(ei, n, k).sample_nodes(2000, 77, 0)
+    assert np.array_equal(nodes[:2000].cpu().numpy(), want)
+    cnt = Counter(frozenset(r) for r in nodes.cpu().numpy().tolist())
+    stat, df, extra = xl.chi_square(cnt, law, M)
+    assert extra == 0 and stat < chi2.ppf(0.999, df), (stat, df)
+    vals = np.array([cnt.get(s_, 0) for s_ in law], np.float64)
+    assert vals.std() / vals.mean() < 0.15
+    (nodes_ref, *_), _ = _batch(ei, ptr, k).sample(M, k, "sample", seed=77)
+    cr = Counter(frozenset(r) for r in nodes_ref.cpu().numpy().tolist())
+    assert xl.chi_square(cr, law, M)[0] > chi2.ppf(0.999, df)
+
+
 def test_uniform_variant_limits(cuda_lib):
     from ugs_b200 import synth
-    ei, ptr = synth.make_batch("proteins", 30, seed=1)  # contains graphs above 64 nodes
+    ei, ptr = synth.barabasi_albert(5000, 3, seed=1)  # above the general path's 4096-vertex limit of this mode
     with pytest.raises(RuntimeError, match="uniform variant"):
         _batch(ei, ptr, 4, variant="uniform")
     ei, ptr = synth.make_batch("mutag", 5, seed=1)
