@@ -349,8 +349,8 @@ def run_config_cases(torch, dev, flush_buf, peak_hbm, with_reference=True, steps
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)  # 2 ms steps: a few of them do not bring the clocks up from idle
     ap.add_argument("--workload", default="zinc", choices=sorted(KM))
     ap.add_argument("--graphs", type=int, default=0, help="graphs per rank (default: workload-specific)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -13,7 +13,9 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
         "smsp__average_warp_latency_issue_stalled_wait.ratio", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "lts__t_sectors.sum",
+        "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "smsp__warps_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[0]
