@@ -119,11 +119,13 @@ struct __align__(16) SmallPre {
 #ifndef PRE_MINB
 #define PRE_MINB 6  // min resident CTAs per SM asked of the compiler: 40 registers, 48 warps/SM (B200 A/B: 5 -> 0.389 ms,
 #endif              // 6 -> 0.373 ms, 7 -> 0.405 ms with spills)
-template <int WARPS>
+// KT > 0 fixes k at compile time: the reachability closure and the weight product unroll.
+template <int WARPS, int KT>
 __global__ void __launch_bounds__(WARPS * 32, PRE_MINB)
 k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, const i64* __restrict__ ptr,
                 i64 G, i64 node_base, int k, const i64* __restrict__ perm, WS w) {
     __shared__ SmallPre sm_all[WARPS];
+    if (KT) k = KT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 g = (i64)blockIdx.x * WARPS + warp;
     if (g >= G) return;
@@ -153,8 +155,9 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
         if (valid) {
             atomicAdd(&s.deg[u], 1u);
             atomicAdd(&s.deg[v], 1u);
-            atomicOr((unsigned long long*)&s.adj[u], 1ull << v);
-            atomicOr((unsigned long long*)&s.adj[v], 1ull << u);
+            // 32-bit halves: a native shared-memory atomic each (the 64-bit OR is a compare-and-swap loop)
+            atomicOr(reinterpret_cast<u32*>(&s.adj[u]) + (v >> 5), 1u << (v & 31));
+            atomicOr(reinterpret_cast<u32*>(&s.adj[v]) + (u >> 5), 1u << (u & 31));
         }
     }
     __syncwarp();
@@ -199,16 +202,33 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
     }
     // s.deg[v] is the multigraph degree again.
 
-    // ---- A.3 order = stable sort by (degree, id): rank by counting -------------------------------
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < n) {
-            const u32 myk = (s.deg[v] << 8) | (u32)v;
-            int rank = 0;
-            for (int t = 0; t < n; ++t) rank += (((s.deg[t] << 8) | (u32)t) < myk) ? 1 : 0;
-            s.order[rank] = (unsigned char)v;
-            s.index_of[v] = (unsigned char)rank;
+    // ---- A.3 order = stable sort by (degree, id): a counting sort over the DISTINCT degree values (a molecule has four
+    //      or five of them): per value two ballots give every vertex of that degree its rank, ids ascending because
+    //      lane order is id order (vertices lane and lane + 32).
+    {
+        const u32 none = 0xFFFFFFFFu;
+        const u32 d0 = (lane < n) ? s.deg[lane] : none, d1 = (lane + 32 < n) ? s.deg[lane + 32] : none;
+        int base = 0;
+        u32 cur = 0;
+        bool first = true;
+        while (base < n) {
+            const u32 c0 = (d0 != none && (first || d0 > cur)) ? d0 : none;
+            const u32 c1 = (d1 != none && (first || d1 > cur)) ? d1 : none;
+            const u32 mn = __reduce_min_sync(FULL_MASK, min(c0, c1));
+            const u32 b0 = __ballot_sync(FULL_MASK, d0 == mn), b1 = __ballot_sync(FULL_MASK, d1 == mn);
+            if (d0 == mn) {
+                const int rank = base + __popc(b0 & lt_mask);
+                s.order[rank] = (unsigned char)lane;
+                s.index_of[lane] = (unsigned char)rank;
+            }
+            if (d1 == mn) {
+                const int rank = base + __popc(b0) + __popc(b1 & lt_mask);
+                s.order[rank] = (unsigned char)(lane + 32);
+                s.index_of[lane + 32] = (unsigned char)rank;
+            }
+            base += __popc(b0) + __popc(b1);
+            cur = mn;
+            first = false;
         }
     }
     __syncwarp();
@@ -227,7 +247,8 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
         s.suf[lane + 32] = xh;
     }
     __syncwarp();
-    // ---- A.4 suffix degree, reachability (bounded BFS as a bitmask closure), weight ---------------
+    // ---- A.4 suffix degree, reachability (bounded BFS as a bitmask closure), weight; the same walk over row(v) also
+    //      classifies the row's multiplicities (every neighbour once / twice / both patterns, no self loop) ----------
     int n0 = 0, n1 = 0, lastv = -1;
     bool self_or_bad = false;
     int mu_min = 99, mu_max = 0;
@@ -239,34 +260,10 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
         if (vi < n) {
             const int v = s.order[vi];
             const int p0 = s.rowptr[v], p1 = s.rowptr[v + 1];
-            for (int p = p0; p < p1; ++p) sd += (s.index_of[s.idx[p]] >= vi) ? 1 : 0;
-            const u64 sufm = s.suf[vi];
-            u64 vis = 1ull << v, expd = 0ull;
-            bool reach = false;
-            for (int it = 0; it < k; ++it) {
-                if (__popcll(vis) >= k) { reach = true; break; }
-                const u64 fr = vis & ~expd;
-                if (!fr) break;
-                const int u = __ffsll((long long)fr) - 1;
-                expd |= 1ull << u;
-                vis |= s.adj[u] & sufm;
-            }
-            if (reach) {
-                const double d = (double)(sd > 1 ? sd : 1);
-                b = 1.0;
-                for (int t = 0; t < k - 1; ++t) b *= d;  // preproc.cpp:228-233
-            }
-            if (b > 0.0) { n0++; lastv = vi; }
-            if (sd > 0) n1++;
-        }
-        s.b[vi] = b;
-        s.sd[vi] = (unsigned short)sd;
-        // multiplicity class of row v = vi's slot (any vertex order works; use v = vi here)
-        if (vi < n) {
-            const int v = vi;
             u64 ones = 0, twos = 0, fours = 0;
-            for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) {
+            for (int p = p0; p < p1; ++p) {
                 const int x = s.idx[p];
+                sd += (s.index_of[x] >= vi) ? 1 : 0;
                 if (x == v) self_or_bad = true;
                 const u64 bit = 1ull << x;
                 const u64 cy0 = ones & bit; ones ^= bit;
@@ -283,7 +280,33 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
                 if (mu == 0) self_or_bad = true;
                 else { mu_min = min(mu_min, mu); mu_max = max(mu_max, mu); }
             }
+            const u64 sufm = s.suf[vi];
+            u64 vis = 1ull << v, expd = 0ull;
+            bool reach = false;
+#pragma unroll
+            for (int it = 0; it < (KT ? KT : 16); ++it) {
+                if (it >= k) break;
+                if (__popcll(vis) >= k) { reach = true; break; }
+                const u64 fr = vis & ~expd;
+                if (!fr) break;
+                const int u = __ffsll((long long)fr) - 1;
+                expd |= 1ull << u;
+                vis |= s.adj[u] & sufm;
+            }
+            if (reach) {
+                const double d = (double)(sd > 1 ? sd : 1);
+                b = 1.0;
+#pragma unroll
+                for (int t = 0; t < (KT ? KT - 1 : 15); ++t) {  // preproc.cpp:228-233: k - 1 sequential multiplies
+                    if (t >= k - 1) break;
+                    b *= d;
+                }
+            }
+            if (b > 0.0) { n0++; lastv = vi; }
+            if (sd > 0) n1++;
         }
+        s.b[vi] = b;
+        s.sd[vi] = (unsigned short)sd;
     }
     __syncwarp();
 #pragma unroll
@@ -874,8 +897,17 @@ extern "C" int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, con
     // kernels are launched with grids sized for the worst case and read the counts from counters[] themselves.
     if ((parts & UGS_PREPROC_SMALL) && n_general < G) {
         constexpr int WARPS = 8;
-        k_preproc_small<WARPS><<<(unsigned)((G + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(
-            row0, row1, ptr, G, node_base, k, perm, w);
+        const unsigned grid = (unsigned)((G + WARPS - 1) / WARPS);
+#define UGS_LAUNCH_PRE(KT_) k_preproc_small<WARPS, KT_><<<grid, WARPS * 32, 0, st>>>(row0, row1, ptr, G, node_base, k, perm, w)
+        switch (k) {
+            case 3: UGS_LAUNCH_PRE(3); break;
+            case 4: UGS_LAUNCH_PRE(4); break;
+            case 5: UGS_LAUNCH_PRE(5); break;
+            case 6: UGS_LAUNCH_PRE(6); break;
+            case 8: UGS_LAUNCH_PRE(8); break;
+            default: UGS_LAUNCH_PRE(0); break;
+        }
+#undef UGS_LAUNCH_PRE
         UGS_LAUNCH_CHECK("k_preproc_small");
     }
     if (!(parts & UGS_PREPROC_GENERAL)) return UGS_OK;
