@@ -43,8 +43,16 @@ __device__ __forceinline__ int popc_m(u64 m) { return __popcll(m); }
 // One sample: root draw (A.5), growth (A.6) and induced-edge count (A.7). MaskT = u32 when the graph has at
 // most 32 vertices (every mask operation is then a single 32-bit instruction), u64 otherwise. KT > 0 fixes k at
 // compile time so that the growth loop unrolls and the Philox refills land at fixed steps.
-template <typename MaskT, int KT>
-__device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& gi, int n, int k, u32 i, u32 c2, u32 c3,
+// the tables one sample needs when the graph's multiplicities are uniform (no CSR rows): 1600 bytes per graph
+struct __align__(16) SlotSamp {
+    u64 adj[64];
+    u64 suf[64];
+    double cum[64];
+    unsigned char order[64];
+};
+
+template <typename MaskT, int KT, typename TabT, bool HAS_ROWS>
+__device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, int n, int k, u32 i, u32 c2, u32 c3,
                                            u32 k0, u32 k1, u64& nlo, u64& nhi, i64& cnt, int& n_incomplete) {
     const int kk = KT ? KT : k;
     Philox4 r = philox4x32_10(i, 0u, c2, c3, k0, k1);
@@ -88,7 +96,7 @@ __device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& 
                 c += popc_m((MaskT)s.adj[v] & S);
             }
             c *= gi.mult;
-        } else {
+        } else if constexpr (HAS_ROWS) {
             for (int j = 0; j < kk; ++j) {
                 const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
                 for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & (MaskT)1);
@@ -100,18 +108,14 @@ __device__ __forceinline__ void sample_one(const SmallSamp& s, const ugs_ginfo& 
     }
 }
 
+// All samples of tiles [t0, t1) of graph g, one thread per sample, by one warp whose shared-memory slice is `s`.
 template <int KT>
-__global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
-k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
-               int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
-               i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
-    __shared__ SmallSamp sm_all[SAMP_WARPS];
-    if (KT) k = KT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const i64 item = (i64)blockIdx.x * SAMP_WARPS + warp;
-    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
-    if (g >= G) return;
-    const int chunk = (int)(item - g * items_per_graph);
+__device__ __forceinline__ void sample_graph_tiles(SmallSamp& s, i64 g, int chunk, int tiles_per_item,
+                                                   const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed,
+                                                   u64 gbase, u32 ibase, int seed_mode, const WS& w,
+                                                   i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr,
+                                                   i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
+    const int lane = threadIdx.x & 31;
     if (chunk == 0 && lane == 0) {
         sample_ptr[g + 1] = (g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
         if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
@@ -138,7 +142,6 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         return;
     }
 
-    SmallSamp& s = sm_all[warp];
     const int n = (int)(ptr[g + 1] - lo);
     const i64 nb = lo - node_base;
 #pragma unroll
@@ -173,8 +176,8 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
         u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
         i64 cnt = 0;
         if (active) {
-            if (n <= 32) sample_one<u32, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
-            else sample_one<u64, KT>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            if (n <= 32) sample_one<u32, KT, SmallSamp, true>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            else sample_one<u64, KT, SmallSamp, true>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
         }
         const i64 s0 = g * m + (i64)t * 32;
         const int nv = (int)min((i64)32, m - (i64)t * 32);
@@ -220,6 +223,114 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
     if (lane == 0) {
         if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
         if (chunk == 0 && gi.level > 0) atomicAdd(&w.counters[UGS_CTR_RELAXED], 1ull);
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
+k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
+               int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
+               i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
+    __shared__ SmallSamp sm_all[SAMP_WARPS];
+    if (KT) k = KT;
+    const int warp = threadIdx.x >> 5;
+    const i64 item = (i64)blockIdx.x * SAMP_WARPS + warp;
+    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
+    if (g >= G) return;
+    const int chunk = (int)(item - g * items_per_graph);
+    sample_graph_tiles<KT>(sm_all[warp], g, chunk, tiles_per_item, ptr, node_base, m, k, seed, gbase, ibase, seed_mode, w,
+                           nodes_out, edge_ptr, sample_ptr, packed);
+}
+
+// m <= 16 samples per graph (QM9-style completeness runs: m = 10) leave most lanes of a (graph, 32-sample tile) warp
+// idle, so a warp takes 32 / S graphs at once, S = 8 or 16 lanes each: every lane group stages the tables of its own
+// graph and samples it. Graphs that need their CSR rows for the entry count (irregular multiplicities, self loops) do
+// not fit this layout: a warp that holds one handles its graphs one after the other with the code above.
+template <int KT, int S>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
+k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
+                      int seed_mode, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr,
+                      i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
+    constexpr int GPW = 32 / S;
+    constexpr size_t SLICE = (sizeof(SlotSamp) * GPW > sizeof(SmallSamp)) ? sizeof(SlotSamp) * GPW : sizeof(SmallSamp);
+    extern __shared__ __align__(16) unsigned char packed_smem_raw[];  // SAMP_WARPS x SLICE (51 KB for S = 8)
+    unsigned char (*raw)[SLICE] = reinterpret_cast<unsigned char (*)[SLICE]>(packed_smem_raw);
+    if (KT) k = KT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane / S, i = lane - slot * S;
+    const i64 g_first = ((i64)blockIdx.x * SAMP_WARPS + warp) * GPW;
+    if (g_first >= G) return;
+    const i64 g = g_first + slot;
+    const bool valid = g < G;
+    ugs_ginfo gi;
+    gi.cls = -1; gi.mult = 0; gi.level = 0; gi.Z = 0.0; gi.nnz = 0; gi.n_eligible = 0; gi.last_viable = 0;
+    if (valid) gi = w.ginfo[g];
+    if (__any_sync(FULL_MASK, valid && gi.cls == 1 && (gi.mult <= 0 || k > 16))) {
+        for (int sl = 0; sl < GPW && g_first + sl < G; ++sl) {
+            sample_graph_tiles<KT>(*reinterpret_cast<SmallSamp*>(raw[warp]), g_first + sl, 0, 1, ptr, node_base, m, k, seed,
+                                   gbase, ibase, seed_mode, w, nodes_out, edge_ptr, sample_ptr, packed);
+            __syncwarp();
+        }
+        return;
+    }
+    if (valid && i == 0) {
+        sample_ptr[g + 1] = (g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
+        if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
+    }
+    SlotSamp& s = reinterpret_cast<SlotSamp*>(raw[warp])[slot];
+    const bool live = valid && gi.cls == 1;
+    const i64 lo = valid ? ptr[g] : 0;
+    const int n = live ? (int)(ptr[g + 1] - lo) : 0;
+    const i64 nb = lo - node_base;
+    for (int v = i; v < n; v += S) {
+        s.adj[v] = w.adj[nb + v];
+        s.suf[v] = w.suf[nb + v];
+        s.cum[v] = w.cum[nb + v];
+        s.order[v] = (unsigned char)w.order[nb + v];
+    }
+    __syncwarp();
+    const bool narrow = __all_sync(FULL_MASK, n <= 32);
+    const bool active = valid && (i64)i < m;
+    const u64 gidx = gbase + (u64)g;
+    const u64 kseed = seed_mode ? seed + gidx : seed;
+    const u64 cg = seed_mode ? 0ull : gidx;
+    const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
+    int n_incomplete = 0;
+    u64 nlo = ~0ull, nhi = ~0ull;
+    i64 cnt = 0;
+    if (live && active) {
+        if (narrow) sample_one<u32, KT, SlotSamp, false>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+        else sample_one<u64, KT, SlotSamp, false>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+    }
+    if (active && (gi.cls == 0 || gi.cls == 1)) {  // cls 0: n < k, rows of -1 (:132-143); cls 2: the general kernel's
+        const i64 row = g * m + i;
+        if (packed) packed[row] = nlo;
+        edge_ptr[1 + row] = cnt;
+        i64* out = nodes_out + row * k;
+        if (KT > 0 && (KT & 1) == 0 && KT <= 8) {
+            longlong2* o2 = reinterpret_cast<longlong2*>(out);
+#pragma unroll
+            for (int q = 0; q < KT / 2; ++q) {
+                const u32 b0 = (u32)(nlo >> (16 * q)) & 0xFFu, b1 = (u32)(nlo >> (16 * q + 8)) & 0xFFu;
+                o2[q] = make_longlong2((b0 == 0xFFu) ? (i64)-1 : lo + (i64)b0, (b1 == 0xFFu) ? (i64)-1 : lo + (i64)b1);
+            }
+        } else {
+            for (int j = 0; j < k; ++j) {  // k > 16 only reaches here for skipped graphs: every entry is -1
+                const u32 bv = (j >= 16) ? 0xFFu : (u32)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFFull);
+                out[j] = (bv == 0xFFu) ? (i64)-1 : lo + (i64)bv;
+            }
+        }
+    }
+    n_incomplete = __reduce_add_sync(FULL_MASK, n_incomplete);
+    const int n_relaxed = __popc(__ballot_sync(FULL_MASK, live && i == 0 && gi.level > 0));
+    i64 cnt_sum = cnt;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cnt_sum += __shfl_xor_sync(FULL_MASK, cnt_sum, off);
+    if (lane == 0) {
+        if (cnt_sum)
+            atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], (unsigned long long)cnt_sum);
+        if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
+        if (n_relaxed) atomicAdd(&w.counters[UGS_CTR_RELAXED], (unsigned long long)n_relaxed);
     }
 }
 
@@ -1014,7 +1125,40 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
     u64* packed = nullptr;
     if (k <= 8 && scratch && scratch_bytes >= ugs_sample_scratch_bytes(G, m))
         packed = reinterpret_cast<u64*>((char*)scratch + packed_rows_offset(G * m));
-    {
+    if (m <= 16) {
+        // several graphs per warp: 8 lanes per graph up to m = 8, 16 lanes up to m = 16
+        const int S = m <= 8 ? 8 : 16;
+        const int64_t warps = (G + 32 / S - 1) / (32 / S);
+        const unsigned grid = (unsigned)((warps + SAMP_WARPS - 1) / SAMP_WARPS);
+        const size_t slice = (sizeof(SlotSamp) * (32 / S) > sizeof(SmallSamp)) ? sizeof(SlotSamp) * (32 / S) : sizeof(SmallSamp);
+        const size_t psmem = slice * SAMP_WARPS;
+#define UGS_LAUNCH_PACKED(KT_)                                                                                          \
+    do {                                                                                                                \
+        if (S == 8) {                                                                                                   \
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_small_packed<KT_, 8>,                                          \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
+            k_sample_small_packed<KT_, 8><<<grid, SAMP_WARPS * 32, psmem, st>>>(ptr, G, node_base, m, k, seed,          \
+                                                                                 graph_index_base, ibase, seed_mode, w, \
+                                                                                 nodes, edge_ptr, sample_ptr, packed); \
+        } else {                                                                                                        \
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_small_packed<KT_, 16>,                                         \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
+            k_sample_small_packed<KT_, 16><<<grid, SAMP_WARPS * 32, psmem, st>>>(ptr, G, node_base, m, k, seed,         \
+                                                                                  graph_index_base, ibase, seed_mode, w, \
+                                                                                  nodes, edge_ptr, sample_ptr, packed); \
+        }                                                                                                               \
+    } while (0)
+        switch (k) {
+            case 3: UGS_LAUNCH_PACKED(3); break;
+            case 4: UGS_LAUNCH_PACKED(4); break;
+            case 5: UGS_LAUNCH_PACKED(5); break;
+            case 6: UGS_LAUNCH_PACKED(6); break;
+            case 8: UGS_LAUNCH_PACKED(8); break;
+            default: UGS_LAUNCH_PACKED(0); break;
+        }
+#undef UGS_LAUNCH_PACKED
+        UGS_LAUNCH_CHECK("k_sample_small_packed");
+    } else {
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
 #define UGS_LAUNCH_SAMPLE(KT_)                                                                                   \

@@ -313,3 +313,24 @@ def test_general_path_sampler_block_boundaries(cuda_lib):
         ref = _oracle_batch(ei, ptr, 200, k, "global", 11)
         for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
             assert np.array_equal(a.cpu().numpy(), r), (name, k)
+
+
+@pytest.mark.parametrize("m", [1, 5, 8, 9, 10, 16])
+@pytest.mark.parametrize("k", [3, 4, 5, 7])
+def test_small_m_packs_several_graphs_per_warp(cuda_lib, m, k):
+    """m <= 16: a warp samples 2 (m <= 16) or 4 (m <= 8) graphs at once (k_sample_small_packed). Batches with every kind
+    of graph in one warp -- uniform multiplicities, multi-edges / self loops (sequential fallback), graphs smaller than
+    k, graphs above 32 and above 64 vertices (general path) -- bit-exact against the oracle in every mode."""
+    rng = np.random.default_rng(100 * m + k)
+    e1, p1 = random_batch(rng, 37, 1, 45, deg=2.5, weird=True, big=[(5, 120), (9, 70)])
+    from ugs_b200 import synth
+    e2, p2 = synth.make_batch("qm9", 45, seed=m + k)        # uniform multiplicity 2, n <= 29: the packed path proper
+    e3, p3 = synth.make_batch("zinc", 11, seed=m)            # some graphs above 32 vertices: 64-bit masks
+    ei, ptr = synth.concat_batches([(e2, p2), (e1, p1), (e3, p3)])
+    for mode in ("sample", "global"):
+        b = _batch(ei, ptr, k)
+        outs, stats = b.sample(m, k, mode, seed=7)
+        ref = _oracle_batch(ei, ptr, m, k, mode, 7)
+        for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r), (name, mode)
+        assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
