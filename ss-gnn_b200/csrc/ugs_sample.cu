@@ -678,25 +678,18 @@ struct __align__(16) SmallEmit<unsigned short> {  // 5664 bytes per warp: 5 CTAs
 
 // NARROW: k <= 8 and mode "sample" / encoder: staged entry = payload << 6 | l << 3 | j  (16 bits)
 // else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
+// Entries of the samples of tiles [t0, t1) of graph g, by one warp whose shared-memory slice is `s`.
 template <bool NARROW>
-__global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
-k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
-             i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
-             const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-             i64* __restrict__ out_src, const u64* __restrict__ packed) {
+__device__ __forceinline__ void emit_graph_tiles(
+    SmallEmit<typename std::conditional<NARROW, unsigned short, u32>::type>& s, i64 g, int t0, int t1,
+    const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mode, int use_perm, const WS& w,
+    const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
+    i64* __restrict__ out_src, const u64* __restrict__ packed) {
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     constexpr bool NIBBLE = NARROW && (EMIT_NIBBLE != 0);  // k <= 8: two vertices per lmap byte
     constexpr int STAGE_N = (int)(sizeof(SmallEmit<stage_t>::stage) / sizeof(stage_t));
     constexpr int LROW_BYTES = (int)sizeof(SmallEmit<stage_t>::lmap) / 32;
-    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
-    SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
-    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
-    if (g >= G) return;
-    const int chunk = (int)(item - g * items_per_graph);
-    const int ntiles = (int)((m + 31) >> 5);
-    const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
+    const int lane = threadIdx.x & 31;
     if (t0 >= t1) return;
     const ugs_ginfo gi = w.ginfo[g];
     if (gi.cls != 1 || gi.nnz == 0) return;
@@ -707,7 +700,6 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
         const i64 sA = g * m + (i64)t0 * 32, sB = min(g * m + m, g * m + (i64)t1 * 32);
         if (edge_ptr[sA] == edge_ptr[sB]) return;
     }
-    SmallEmit<stage_t>& s = sm_all[warp];
     const i64 c0 = w.cstart[g];
     const i32* __restrict__ gcol = w.csr_col + 2 * c0;
     {
@@ -906,6 +898,179 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
             for (int j = 0; j < 16; ++j)
                 if (j < k) lrow[((nb4[j >> 2] >> (8 * (j & 3))) & 0xFFu) >> (NIBBLE ? 1 : 0)] = (unsigned char)0xFF;
         }
+    }
+}
+
+template <bool NARROW>
+__global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
+k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
+             i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
+             const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
+             i64* __restrict__ out_src, const u64* __restrict__ packed) {
+    typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
+    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
+    SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
+    const int warp = threadIdx.x >> 5;
+    const i64 item = (i64)blockIdx.x * EMIT_WARPS + warp;
+    const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
+    if (g >= G) return;
+    const int chunk = (int)(item - g * items_per_graph);
+    const int ntiles = (int)((m + 31) >> 5);
+    const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
+    emit_graph_tiles<NARROW>(sm_all[warp], g, t0, t1, ptr, node_base, m, k, mode, use_perm, w, nodes, edge_ptr, out_u, out_v,
+                             out_src, packed);
+}
+
+// m <= 16 (QM9-style runs): 32 / S graphs per warp, S = 8 or 16 lanes each, like k_sample_small_packed. Every lane group
+// stages the CSR of its own graph (at most PK_ENT entries; payload = source column relative to the FIRST graph of the
+// warp, 10 bits); the output of the warp's graphs is one contiguous run, so staging and the coalesced flush work as in
+// the one-graph kernel. k <= 8, mode "sample" / encoder, graph-contiguous columns, rows packed by the sampling kernel.
+// A warp holding a general-path graph or a graph with more than PK_ENT entries handles its graphs one after the other.
+#define PK_ENT 256
+template <int GPW>
+struct __align__(16) PackedEmit {
+    unsigned short stage[NIB_STAGE];
+    unsigned char lmap[32][NIB_STRIDE];
+    u32 rowrange[GPW][64];
+    unsigned short ent[GPW][PK_ENT];
+};
+
+template <int S>
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 4)
+k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, WS w,
+                    const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr, i64* __restrict__ out_u,
+                    i64* __restrict__ out_v, i64* __restrict__ out_src, const u64* __restrict__ packed) {
+    constexpr int GPW = 32 / S;
+    constexpr size_t SLICE = sizeof(PackedEmit<GPW>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<GPW>)
+                                                                                            : sizeof(SmallEmit<unsigned short>);
+    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slice = emit_smem_raw + (size_t)warp * SLICE;
+    const int slot = lane / S, i = lane - slot * S;
+    const i64 g_first = ((i64)blockIdx.x * EMIT_WARPS + warp) * GPW;
+    if (g_first >= G) return;
+    const i64 g_end = min(G, g_first + GPW);
+    const i64 g = g_first + slot;
+    const bool valid = g < G;
+    ugs_ginfo gi;
+    gi.cls = -1; gi.nnz = 0; gi.mult = 0; gi.level = 0; gi.Z = 0.0; gi.n_eligible = 0; gi.last_viable = 0;
+    if (valid) gi = w.ginfo[g];
+    const i64 tile_lo = edge_ptr[g_first * m], tile_end = edge_ptr[g_end * m];
+    if (tile_end == tile_lo) return;
+    const i64 c0 = w.cstart[g_first];
+    if (__any_sync(FULL_MASK, valid && (gi.cls == 2 || (gi.cls == 1 && gi.nnz > PK_ENT))) || w.cstart[g_end] - c0 > 1023) {
+        for (i64 gg = g_first; gg < g_end; ++gg) {
+            emit_graph_tiles<true>(*reinterpret_cast<SmallEmit<unsigned short>*>(slice), gg, 0, 1, ptr, node_base, m, k, mode,
+                                   0, w, nodes, edge_ptr, out_u, out_v, out_src, packed);
+            __syncwarp();
+        }
+        return;
+    }
+    PackedEmit<GPW>& s = *reinterpret_cast<PackedEmit<GPW>*>(slice);
+    const bool live = valid && gi.cls == 1 && gi.nnz > 0;
+    {
+        const i64 lo = valid ? ptr[g] : 0;
+        const int n = live ? (int)(ptr[g + 1] - lo) : 0;
+        const i64 cg = valid ? w.cstart[g] : 0;
+        const u32* rp = w.rowptr + (lo - node_base) + g;
+        const i32* ci = w.csr_idx + 2 * cg;
+        const i32* gc = w.csr_col + 2 * cg;
+        for (int v = i; v < n; v += S) s.rowrange[slot][v] = (rp[v] << 1) | (rp[v + 1] << 17);
+        const int nnz = live ? gi.nnz : 0;
+        for (int p = i; p < nnz; p += S) s.ent[slot][p] = (unsigned short)((u32)ci[p] | ((u32)(gc[p] - (i32)c0) << 6));
+        u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
+#pragma unroll
+        for (int q = 0; q < NIB_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    // this lane's sample: lanes without one (i >= m, graph beyond the batch) get the empty range that keeps the per-lane
+    // start offsets monotone (= the start of the next graph's first sample)
+    const bool has = valid && (i64)i < m;
+    const i64 rowid = has ? g * m + i : -1;
+    const i64 my_lo = has ? edge_ptr[rowid] : (valid ? edge_ptr[(g + 1) * m] : tile_end);
+    const i64 my_end = has ? edge_ptr[rowid + 1] : my_lo;
+    const bool walk = has && live && (my_end > my_lo);
+    unsigned char* lrow = &s.lmap[lane][0];
+    const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent[slot]);
+    const u32* rr_tab = s.rowrange[slot];
+    u32 nb2[2] = {~0u, ~0u};
+    if (walk) {
+        const u64 prow = packed[rowid];
+        nb2[0] = (u32)prow; nb2[1] = (u32)(prow >> 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < k) {
+                const u32 v = (nb2[j >> 2] >> (8 * (j & 3))) & 63u;
+                const u32 sh = (v & 1u) * 4u;
+                lrow[v >> 1] = (unsigned char)((lrow[v >> 1] & ~(0xFu << sh)) | ((u32)j << sh));
+            }
+    }
+    const int tile_total = (int)min(tile_end - tile_lo, (i64)0x7fffffff);
+    const int nsplit = (tile_total + NIB_STAGE - 1) / NIB_STAGE;
+    const int cap_eff = (nsplit <= 1) ? NIB_STAGE : min(NIB_STAGE, tile_total / nsplit + 48);
+    int sa = 0;
+    while (sa < 32) {
+        const i64 base = __shfl_sync(FULL_MASK, my_lo, sa);
+        const u32 fits = __ballot_sync(FULL_MASK, lane >= sa && (my_end - base) <= cap_eff);
+        const u32 nofit = ~fits & ~((1u << sa) - 1u);
+        int sb = nofit ? (__ffs(nofit) - 1) : 32;
+        if (sb == sa) sb = sa + 1;  // a single sample always fits the staging buffer (<= PK_ENT entries)
+        const int run = (int)(((sb == 32) ? tile_end : __shfl_sync(FULL_MASK, my_lo, sb & 31)) - base);
+        if (walk && lane >= sa && lane < sb) {
+            unsigned short* st = s.stage + (int)(my_lo - base);
+            u32 pj = 0u;
+            int j = 0;
+            u32 rr = rr_tab[nb2[0] & 0xFFu];
+            u32 p = rr & 0xFFFFu, pe = rr >> 16;
+#pragma nounroll
+            while (true) {
+                if (p == pe) {
+                    if (++j == k) break;
+                    const u32 wsel = (j < 4) ? nb2[0] : nb2[1];
+                    rr = rr_tab[(wsel >> (8 * (j & 3))) & 0xFFu];
+                    p = rr & 0xFFFFu; pe = rr >> 16;
+                    pj++;
+                }
+                asm volatile("" ::: "memory");
+                if (p != pe) {
+                    const u32 e = *reinterpret_cast<const unsigned short*>(entb + p);
+                    const u32 x = e & 63u;
+                    const u32 l = ((u32)lrow[x >> 1] >> ((x & 1u) * 4u)) & 0xFu;
+                    if (l != 0xFu) *st++ = (unsigned short)((e & 0xFFC0u) + (l << 3) + pj);
+                    p += 2;
+                }
+            }
+        }
+        __syncwarp();
+        if (mode == UGS_MODE_ENCODER) {
+            const int rel_lo = (lane >= sa && lane < sb) ? (int)(my_lo - base) : 0x7fffffff;
+            for (int e0 = 0; e0 < run; e0 += 32) {
+                const int e = e0 + lane;
+                int a = sa;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int cand = a + step;
+                    const int off = __shfl_sync(FULL_MASK, rel_lo, cand & 31);
+                    if (cand < sb && off <= e) a = cand;
+                }
+                if (e < run) {
+                    const u32 pk = s.stage[e];
+                    const i64 ik = ((g_first + a / S) * m + (a % S)) * (i64)k;  // the owning sample's row
+                    out_u[base + e] = ik + (i64)(pk & 7u);
+                    out_v[base + e] = ik + (i64)((pk >> 3) & 7u);
+                    out_src[base + e] = c0 + (i64)(pk >> 6);
+                }
+            }
+        } else {
+            for (int e = lane; e < run; e += 32) {
+                const u32 pk = s.stage[e];
+                out_u[base + e] = (i64)(pk & 7u);
+                out_v[base + e] = (i64)((pk >> 3) & 7u);
+                out_src[base + e] = c0 + (i64)(pk >> 6);
+            }
+        }
+        __syncwarp();
+        sa = sb;
     }
 }
 
@@ -1258,7 +1423,23 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
         small_items(m, G, &tpi, &ipg);
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS);
-        if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
+        if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER) && m <= 16 && packed && !use_perm) {
+            // several graphs per warp (the rows must be the packed ones ugs_sample_batch left behind)
+            const int S = m <= 8 ? 8 : 16;
+            const int64_t warps = (G + 32 / S - 1) / (32 / S);
+            const unsigned pgrid = (unsigned)((warps + EMIT_WARPS - 1) / EMIT_WARPS);
+            if (S == 8) {
+                const size_t sl = sizeof(PackedEmit<4>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<4>) : sizeof(SmallEmit<unsigned short>);
+                UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
+                k_emit_small_packed<8><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
+                                                                                       out_u, out_v, edge_src_out, packed);
+            } else {
+                const size_t sl = sizeof(PackedEmit<2>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<2>) : sizeof(SmallEmit<unsigned short>);
+                UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
+                k_emit_small_packed<16><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
+                                                                                        out_u, out_v, edge_src_out, packed);
+            }
+        } else if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
             const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,

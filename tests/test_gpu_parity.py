@@ -334,3 +334,10 @@ def test_small_m_packs_several_graphs_per_warp(cuda_lib, m, k):
         for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
             assert np.array_equal(a.cpu().numpy(), r), (name, mode)
         assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
+    if k <= 8:  # encoder mode (batch-level ids s*k + local, ss_gnn.py:461-462) through the packed emission kernel
+        b = _batch(ei, ptr, k)
+        (n_s, e_s, p_s, _, s_s), _ = b.sample(m, k, "sample", seed=7)
+        (n_e, e_e, p_e, _, s_e), _ = b.sample(m, k, "encoder", seed=7)
+        counts = (p_s[1:] - p_s[:-1])
+        off = torch.repeat_interleave(torch.arange(n_s.shape[0], device=e_s.device), counts) * k
+        assert torch.equal(e_e, e_s + off.unsqueeze(0)) and torch.equal(s_e, s_s) and torch.equal(p_e, p_s)
