@@ -618,8 +618,22 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
             }
         }
         __syncthreads();
-        // ---- A.3 order: sort keys (degree << 32 | id) ---------------------------------------------
-        {
+        // ---- A.3 order = stable sort by (degree, id). Up to 2048 vertices (every PROTEINS-sized graph): rank by counting
+        //      -- position of v = number of vertices with a smaller (degree, id) key, degrees staged in shared memory,
+        //      two barriers; larger graphs: bitonic network over (degree << 32 | id) (55+ barriers) ------------------
+        if (n <= 2048) {
+            u32* sdeg = reinterpret_cast<u32*>(sbuf);
+            for (int v = tid; v < n; v += T_) sdeg[v] = (u32)iof[v];
+            __syncthreads();
+            for (int v = tid; v < n; v += T_) {
+                const u32 dv = sdeg[v];
+                int rank = 0;
+                for (int u = 0; u < v; ++u) rank += (sdeg[u] <= dv) ? 1 : 0;      // smaller id: ties come first
+                for (int u = v + 1; u < n; ++u) rank += (sdeg[u] < dv) ? 1 : 0;
+                ord[rank] = v;
+                iof[v] = rank;
+            }
+        } else {
             u64* keys = (u64*)cm;
             for (int v = tid; v < n; v += T_) keys[v] = (((u64)(u32)iof[v]) << 32) | (u32)v;
             __syncthreads();
