@@ -64,16 +64,33 @@ __global__ void k_seg_fast(const i64* __restrict__ row0, i64 E, const i64* __res
     cstart[g] = lo;
 }
 
+// SEG: the fast segmentation (k_seg_fast) done by the classifying thread itself -- the column range of graph g by two
+// interleaved binary searches over the columns -- so that a batch costs one launch instead of two here.
+template <bool SEG>
 __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_lt_k, const i64* __restrict__ fast_row0,
-                           WS w) {
+                           i64 E, WS w) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
     i64 n = ptr[g + 1] - ptr[g];
-    i64 nc = w.cstart[g + 1] - w.cstart[g];
+    i64 c_lo, c_hi;
+    if (SEG) {
+        const i64 ta = ptr[g], tb = ptr[g + 1];
+        i64 lo_a = 0, hi_a = E, lo_b = 0, hi_b = E;  // first column whose source is >= ta / >= tb
+        while (lo_a < hi_a || lo_b < hi_b) {
+            if (lo_a < hi_a) { const i64 mid = (lo_a + hi_a) >> 1; if (fast_row0[mid] >= ta) hi_a = mid; else lo_a = mid + 1; }
+            if (lo_b < hi_b) { const i64 mid = (lo_b + hi_b) >> 1; if (fast_row0[mid] >= tb) hi_b = mid; else lo_b = mid + 1; }
+        }
+        c_lo = lo_a; c_hi = lo_b;
+        w.cstart[g] = c_lo;
+        if (g == G - 1) { w.cstart[G] = c_hi; w.cstart[G + 1] = E; }
+    } else {
+        c_lo = w.cstart[g]; c_hi = w.cstart[g + 1];
+    }
+    i64 nc = c_hi - c_lo;
     ugs_ginfo gi;
     gi.Z = 0.0; gi.nnz = 0; gi.level = -1; gi.n_eligible = 0; gi.last_viable = -1; gi.mult = 0;
     if (n < 0) atomicOr(&w.counters[UGS_CTR_UNSORTED], 2ull);  // ptr not non-decreasing
-    if (nc < 0 || (g == 0 && w.cstart[0] != 0) || (g == G - 1 && w.cstart[G] != w.cstart[G + 1]))
+    if (nc < 0 || (g == 0 && c_lo != 0) || (g == G - 1 && c_hi != (SEG ? E : w.cstart[G + 1])))
         atomicOr(&w.counters[UGS_CTR_UNSORTED], 4ull);  // bounds do not tile [0,E): not graph-contiguous
     if (n <= 0 || (skip_lt_k && n < k)) {  // ugs_sampler_batch_extension.cpp:132 (batch driver only)
         gi.cls = 0;
@@ -82,7 +99,7 @@ __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_l
         // a column of ANOTHER graph inside this range (batch not graph-contiguous) would otherwise be lost silently.
         if (fast_row0) {
             const i64 lo_ = ptr[g], hi_ = ptr[g + 1];
-            for (i64 c = w.cstart[g]; c < w.cstart[g + 1]; ++c) {
+            for (i64 c = c_lo; c < c_hi; ++c) {
                 const i64 u = fast_row0[c];
                 if (u < lo_ || u >= hi_) { atomicOr(&w.counters[UGS_CTR_UNSORTED], 8ull); break; }
             }
@@ -825,6 +842,12 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
     WS w = ws_views(workspace, L);
     UGS_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(i64) * UGS_CTR_COUNT, st));
     const int T = 256;
+    if (fast && !perm && G > 0) {
+        // graph-contiguous columns: the classifying kernel finds the column ranges itself (one launch)
+        k_classify<true><<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, edge_index, E, w);
+        UGS_LAUNCH_CHECK("k_classify");
+        return UGS_OK;
+    }
     if (fast && !perm) {
         k_seg_fast<<<(unsigned)((G + 2 + T - 1) / T), T, 0, st>>>(edge_index, E, ptr, G, w.cstart);
         UGS_LAUNCH_CHECK("k_seg_fast");
@@ -837,7 +860,7 @@ extern "C" int ugs_segment_batch(const int64_t* edge_index, int64_t E, const int
         UGS_LAUNCH_CHECK("k_seg_bounds");
     }
     if (G > 0) {
-        k_classify<<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, (fast && !perm) ? edge_index : nullptr, w);
+        k_classify<false><<<(unsigned)((G + T - 1) / T), T, 0, st>>>(ptr, G, k, skip_lt_k, nullptr, E, w);
         UGS_LAUNCH_CHECK("k_classify");
     }
     return UGS_OK;
