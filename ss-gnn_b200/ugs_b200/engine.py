@@ -497,9 +497,12 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
         off_s = (lay.total_bytes + 255) & ~255
         off_e = off_s + ((sbytes + 255) & ~255)
         tmp = torch.empty(off_e + 24 * cap, dtype=torch.uint8, device=dev)
-        nodes = torch.empty((B, k), dtype=torch.int64, device=dev)
-        edge_ptr = torch.empty(B + 1, dtype=torch.int64, device=dev)
-        sample_ptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+        # the three outputs whose sizes do not depend on the samples share one allocation (so that a caller who wants
+        # them on the host needs one copy): nodes | edge_ptr | sample_ptr
+        fixed = torch.empty(B * k + (B + 1) + (G + 1), dtype=torch.int64, device=dev)
+        nodes = fixed[:B * k].view(B, k)
+        edge_ptr = fixed[B * k:B * k + B + 1]
+        sample_ptr = fixed[B * k + B + 1:]
         slots = _fused_tls.__dict__.setdefault("info", {})
         hi = slots.get(dev.index)
         if hi is None:
@@ -522,13 +525,15 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
         stats = dict(n_graphlets=B, n_edge_entries=total, n_incomplete=int(info[CTR["incomplete"]]),
                      n_relaxed_graphs=int(info[CTR["relaxed"]]), n_skipped_graphs=n_skipped,
                      n_general_graphs=int(info[CTR["n_general"]]), n_trials=(G - n_skipped) * m)
-        edge_index_out = torch.empty((2, total), dtype=torch.int64, device=dev)
-        edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+        edges = torch.empty(3 * total, dtype=torch.int64, device=dev)  # edge_index rows | edge_src, one allocation
+        edge_index_out = edges[:2 * total].view(2, total)
+        edge_src = edges[2 * total:]
         if total > 0:
             rc = L.ugs_fused_finish(base + off_e, base + off_e + 8 * cap, base + off_e + 16 * cap, total,
                                     edge_index_out.data_ptr(), edge_src.data_ptr(), stream)
             if rc != 0:
                 _lib.check(rc)
+        _fused_tls.last_buffers = (fixed, edges)  # for ugs_sampler (same thread): two device->host copies instead of five
     finally:
         if switch:
             torch.cuda.set_device(prev)

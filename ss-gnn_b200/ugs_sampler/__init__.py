@@ -295,13 +295,31 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
                 and _engine.fused_eligible(E, G, NT, int(m_per_graph), int(k))):
             # DataLoader-sized call: the whole pipeline as one library call with one host round trip
             r = _engine.sample_batch_fused(ei, p, int(m_per_graph), int(k), mode, int(seed), pb[0], NT)
-        if r is None:
+        bufs = None
+        if r is not None:  # fused path: the two device allocations behind the five outputs
+            bufs = getattr(_engine._fused_tls, "last_buffers", None)
+            _engine._fused_tls.last_buffers = None
+        else:
             b = _engine.DeviceBatch(ei, p, int(k), pb[0], NT, variant=variant)
             r = b.sample(int(m_per_graph), int(k), mode, int(seed))
             if _debug_on():
                 _debug_report(b, r[0][0], int(m_per_graph), int(k), with_cache_line=True)
         outs, _stats = r
         sample_batch.last_stats = _stats
+        if (bufs is not None and not _want_cuda_out(edge_index)
+                and 8 * (bufs[0].numel() + bufs[1].numel()) < _PACKED_MIN_BYTES):
+            # fused small-batch path: the five outputs are views of two device allocations -> two copies, five host views
+            fixed, edges = bufs
+            h_fixed = torch.empty(fixed.shape, dtype=torch.int64, pin_memory=True)
+            h_edges = torch.empty(edges.shape, dtype=torch.int64, pin_memory=True)
+            h_fixed.copy_(fixed, non_blocking=True)
+            h_edges.copy_(edges, non_blocking=True)
+            B, kk, total, Gn = outs[0].shape[0], outs[0].shape[1], outs[4].shape[0], outs[3].shape[0]
+            torch.cuda.current_stream().synchronize()
+            _to_host_batch.last_delivery = "plain int64 copy (two buffers)"
+            _to_host_batch.last_d2h_bytes = 8 * (fixed.numel() + edges.numel())
+            return (h_fixed[:B * kk].view(B, kk), h_edges[:2 * total].view(2, total), h_fixed[B * kk:B * kk + B + 1],
+                    h_fixed[B * kk + B + 1:B * kk + B + 1 + Gn], h_edges[2 * total:])
         return tuple(outs if _want_cuda_out(edge_index) else _to_host_batch(outs, mode, int(k)))
 
 
