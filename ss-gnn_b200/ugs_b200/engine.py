@@ -448,7 +448,7 @@ class DeviceBatch:
 
 
 # ---- small batches: one library call, one host round trip (csrc/ugs_fused.cu) --------------------------------------
-FUSED_MAX_BYTES = 256 << 20   # worst-case output (24 bytes x 2E x m) up to which the fused path is taken
+FUSED_MAX_BYTES = 1 << 30     # worst-case output (24 bytes x 2E x m) up to which the fused path is taken
 _fused_tls = threading.local()  # per thread and device: (pinned int64[64] tensor for the counters, its numpy view)
 
 
