@@ -501,6 +501,7 @@ k_preproc_general(const i64* __restrict__ row0, const i64* __restrict__ row1, co
         const i64 lo = ptr[g];
         const int n = (int)(ptr[g + 1] - lo);
         if (n > UGS_LARGE_N) continue;  // large graphs: k_preproc_large (whole GPU per graph)
+        if (w.ginfo[g].level >= 0) continue;  // already preprocessed by k_preproc_medium (shared-memory kernel)
         const i64 c0 = w.cstart[g];
         const i64 nc = w.cstart[g + 1] - c0;
         const i64 nb = lo - node_base;
@@ -911,6 +912,8 @@ extern "C" int ugs_batch_info_end(void) {
 
 int ugs_launch_preproc_large(const i64* row0, const i64* row1, const i64* ptr, i64 node_base, int k, const i64* perm,
                              i64 n_large, WS& w, cudaStream_t st);  // ugs_preproc_large.cu
+int ugs_launch_preproc_medium(const i64* row0, const i64* row1, const i64* ptr, i64 G, i64 node_base, int k,
+                              const i64* perm, i64 n_general, WS& w, cudaStream_t st);  // ugs_preproc_medium.cu
 
 extern "C" int ugs_preproc_batch(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G,
                                  int64_t node_base, int k, const int64_t* perm, int64_t n_general, int64_t n_large,
@@ -953,6 +956,10 @@ extern "C" int ugs_preproc_batch_parts(const int64_t* edge_index, int64_t E, con
         if (rc != UGS_OK) return rc;
     }
     if (n_general < 0 || n_general > n_large) {
+        // PROTEINS-sized graphs first, in shared memory; k_preproc_general then takes whatever is left (it skips graphs
+        // whose ginfo.level is already set)
+        const int rc = ugs_launch_preproc_medium(row0, row1, ptr, G, node_base, k, perm, n_general, w, st);
+        if (rc != UGS_OK) return rc;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

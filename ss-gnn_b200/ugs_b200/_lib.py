@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.environ.get("UGS_B200_LIB") or os.path.join(HERE, "libugs_b200.so")  # override: A/B kernel variants
-SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_hostdeliver.cpp", "ugs_fused.cu", "ugs_variants.cu", "ugs_uniform_general.cu", "ugs_apx.cu", "ugs_capi.cu"]
+SOURCES = ["ugs_preproc.cu", "ugs_preproc_large.cu", "ugs_preproc_medium.cu", "ugs_sortcols.cu", "ugs_sample.cu", "ugs_gather.cu", "ugs_rwr.cu", "ugs_enum.cu", "ugs_presample.cu", "ugs_wl.cu", "ugs_hostio.cu", "ugs_hostdeliver.cpp", "ugs_fused.cu", "ugs_variants.cu", "ugs_uniform_general.cu", "ugs_apx.cu", "ugs_capi.cu"]
 HEADERS = [os.path.join(CSRC, "ugs_common.cuh"), os.path.join(CSRC, "ugs_hostio.h"), os.path.join(REPO, "include", "ugs_b200.h")]
 
 EXPORTS = [
