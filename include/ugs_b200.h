@@ -124,6 +124,8 @@ typedef struct ugs_ginfo {
 #define UGS_CTR_EMIT_OVERFLOW 15 /* samples ugs_eps_emit_edges could not emit (more than 1024 induced columns on the
                                     general path, or counts that do not match edge_ptr): their slice of the output is
                                     left untouched -- the caller must treat a non-zero value as an error      */
+#define UGS_CTR_N_NOT_MEDIUM 48  /* general-path graphs above the shared-memory kernels' size (more than 1024 nodes or
+                                    3072 columns): 0 lets the global-memory general-path kernels return at once */
 #define UGS_CTR_COUNT 64         /* int64 words in counters[]                                             */
 #define UGS_CTR_EARLY_TOTAL 16   /* [16, 48): partial sums of the per-sample entry counts, added up by the sampling
                                     kernels themselves (32 addresses to spread the atomics); their sum is the total
@@ -241,13 +243,18 @@ int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m,
  * is synchronised once, after counters[] has been copied to h_info (pinned host memory, UGS_CTR_COUNT int64):
  * h_info[UGS_CTR_TOTAL_EDGES] = Ebar; a non-zero h_info[UGS_CTR_UNSORTED] means the batch needs the staged path and no
  * output is valid. ugs_fused_finish narrows the bound-sized arrays into edge_index_out[2,Ebar] / edge_src_out[Ebar].
- * Outputs are bit-identical to the staged sequence. */
+ * Outputs are bit-identical to the staged sequence.
+ * assume_no_general != 0 leaves the general-path kernels out of the queue (five launches that would return at once --
+ * ~3 us each in a 0.1 ms chain -- when the batch has no graph above 64 nodes / 384 columns, as every MUTAG / QM9 / ZINC
+ * batch): the caller must then check h_info[UGS_CTR_N_GENERAL]; non-zero voids the outputs and the call has to be
+ * repeated with assume_no_general = 0. */
 int64_t ugs_fused_capacity(int64_t E, int64_t m);
 int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
                            int64_t total_nodes, int64_t m, int k, int mode, uint64_t seed, uint64_t graph_index_base,
                            uint64_t sample_index_base, int seed_mode, void* workspace, const ugs_layout* L,
                            void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
-                           int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info, void* stream);
+                           int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info,
+                           int assume_no_general, void* stream);
 int ugs_fused_finish(const int64_t* ei_u, const int64_t* ei_v, const int64_t* ei_src, int64_t total,
                      int64_t* edge_index_out, int64_t* edge_src_out, void* stream);
 

@@ -31,7 +31,7 @@ for it in range(40):
         base = tmp.data_ptr(); vp = ctypes.c_void_p
         args = (_ptr(d_ei), E, _ptr(d_ptr), G, 0, NT, m, k, 0, 42, 0, 0, 0, vp(base), ctypes.byref(lay), vp(base + off_s), sbytes,
                 _ptr(nodes), _ptr(edge_ptr), _ptr(sample_ptr), vp(base + off_e), vp(base + off_e + 8 * cap), vp(base + off_e + 16 * cap),
-                cap, vp(hi.data_ptr()), _stream()); t = T("marshal", t)
+                cap, vp(hi.data_ptr()), int(os.environ.get("ASSUME_NO_GENERAL", "0")), _stream()); t = T("marshal", t)
         rc = L.ugs_sample_batch_fused(*args); t = T("C call (launches+sync)", t)
         info = hi[:16].tolist(); t = T("tolist", t)
         total = int(info[4])

@@ -157,6 +157,21 @@ __device__ __forceinline__ int warp_cdf_search(const double* __restrict__ cm, in
     return ball ? lo + __ffs(ball) - 1 : n - 1;
 }
 
+// Asynchronous global -> shared copies (LDGSTS): a thread issues any number of them without waiting, so a CTA staging
+// several tables has all their loads in flight at once; cp_async_wait_all + __syncthreads() makes them visible.
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// PROTEINS-sized general-path graphs: their tables fit a CTA's shared memory (k_preproc_medium, k_sample_medium)
+__host__ __device__ __forceinline__ bool ugs_is_medium(long long n, long long nc) { return n <= 1024 && nc <= 3072; }
+
 // internal entry points shared between translation units
 int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
                           uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,

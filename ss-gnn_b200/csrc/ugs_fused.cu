@@ -29,7 +29,7 @@ extern "C" int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, cons
                                       int seed_mode, void* workspace, const ugs_layout* L, void* scratch,
                                       size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
                                       int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info,
-                                      void* stream_) {
+                                      int assume_no_general, void* stream_) {
     if (!workspace || !L || !h_info) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (G <= 0 || m <= 0) return ugs_set_error(UGS_EINVAL, "the fused path needs G > 0 and m > 0");
     if (cap < ugs_fused_capacity(E, m)) return ugs_set_error(UGS_EINVAL, "output capacity below m * 2E");
@@ -38,7 +38,11 @@ extern "C" int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, cons
     int rc = ugs_segment_batch(edge_index, E, ptr, G, k, 1, 1, nullptr, workspace, L, stream_);
     if (rc != UGS_OK) return rc;
     // general-path kernels only where a general-path graph can exist at all (host-known bounds)
-    const bool maybe_general = (k > 16) || (total_nodes > UGS_SMALL_MAX_N) || (E > UGS_SMALL_MAX_COLS);
+    // assume_no_general: the caller's guess (the previous batch of this data set had none) drops the five general-path
+    // launches -- they return at once when the device count is zero, but cost ~3 us each in a 0.1 ms chain. The guess is
+    // checked by the caller against h_info[UGS_CTR_N_GENERAL]: non-zero means the outputs are void and the call must be
+    // repeated without the assumption.
+    const bool maybe_general = !assume_no_general && ((k > 16) || (total_nodes > UGS_SMALL_MAX_N) || (E > UGS_SMALL_MAX_COLS));
     const int64_t ngen = maybe_general ? -1 : 0;
     const int64_t nlarge = (maybe_general && total_nodes > UGS_LARGE_N) ? -1 : 0;
     rc = ugs_preproc_batch_parts(edge_index, E, ptr, G, node_base, k, nullptr, ngen, nlarge, UGS_PREPROC_ALL, workspace,
@@ -48,7 +52,7 @@ extern "C" int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, cons
                                UGS_VARIANT_REF, ngen, total_nodes, workspace, L, scratch, scratch_bytes, nodes,
                                edge_ptr, sample_ptr, nullptr, stream_, /*counters_fresh=*/true);
     if (rc != UGS_OK) return rc;
-    rc = ugs_emit_edges_packed(ptr, G, node_base, m, k, mode, 0, ngen, workspace, L, nodes, edge_ptr, cap, ei_u, ei_src,
+    rc = ugs_emit_edges_packed(ptr, G, node_base, m, k, mode, 0, assume_no_general ? -2 : ngen, workspace, L, nodes, edge_ptr, cap, ei_u, ei_src,
                                scratch, scratch_bytes, stream_);
     if (rc != UGS_OK) return rc;
     UGS_CUDA_CHECK(cudaMemcpyAsync(h_info, (const char*)workspace + L->counters, sizeof(i64) * UGS_CTR_COUNT,

@@ -112,6 +112,7 @@ __global__ void k_classify(const i64* __restrict__ ptr, i64 G, int k, int skip_l
         w.glist[slot] = (i32)g;
         atomicMax(&w.counters[UGS_CTR_MAX_N_GENERAL], (unsigned long long)n);
         if (n > UGS_LARGE_N) w.llist[atomicAdd(&w.counters[UGS_CTR_N_LARGE], 1ull)] = (i32)g;
+        if (!ugs_is_medium(n, nc)) atomicAdd(&w.counters[UGS_CTR_N_NOT_MEDIUM], 1ull);
     }
     w.ginfo[g] = gi;
 }

@@ -346,59 +346,21 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
 // growth the slice is wiped with vector stores and reused as the membership bitmap of S for the entry count.
 #define GEN_WORK_CHUNK 4  // samples a warp claims per atomic on the work counter
 
-#ifndef GEN_MINB
-#define GEN_MINB 5  // resident CTAs per SM the kernel is compiled for (51 registers -> 40 warps per SM)
-#endif
-__global__ void __launch_bounds__(256, GEN_MINB)
-k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
-                 int seed_mode, i64 n_general, int bm_words, int bm_stride, WS w, i64* __restrict__ nodes_out,
-                 i64* __restrict__ edge_ptr) {
-    extern __shared__ __align__(16) u32 bm_all[];
-    if (n_general < 0) n_general = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
-    if (n_general == 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    u32* bm = bm_all + (size_t)warp * bm_stride;  // [bm_words] cut bitmap (bm_words is a multiple of 32)
-    u32* bc = bm + bm_words;                      // [bm_words / 32] set bits per block of 32 words
-    for (int i = lane; i < bm_stride; i += 32) bm[i] = 0;
-    __syncwarp();
-    const i64 total = n_general * m;
-    unsigned long long n_incomplete = 0, n_relaxed = 0, n_entries = 0;
-
-    // a claim covers GEN_WORK_CHUNK samples when there is plenty of work, one sample when every warp gets only a few
-    const int chunk = (total >= (i64)gridDim.x * (blockDim.x >> 5) * (2 * GEN_WORK_CHUNK)) ? GEN_WORK_CHUNK : 1;
-    while (true) {
-        i64 tbase = 0;
-        if (lane == 0) tbase = (i64)atomicAdd(&w.counters[UGS_CTR_WORK], (unsigned long long)chunk);
-        tbase = __shfl_sync(FULL_MASK, tbase, 0);
-        if (tbase >= total) break;
-        const i64 tend = min(total, tbase + chunk);
-    for (i64 t = tbase; t < tend; ++t) {
-        const i64 gi_ = t / m;
-        const i64 i = t - gi_ * m;
-        const i64 g = w.glist[gi_];
-        const ugs_ginfo gi = w.ginfo[g];
-        const i64 lo = ptr[g];
-        const int n = (int)(ptr[g + 1] - lo);
-        const i64 nb = lo - node_base;
-        const u32* __restrict__ rp = w.rowptr + nb + g;
-        const i32* __restrict__ ord = w.order + nb;
-        const i32* __restrict__ iof = w.index_of + nb;
-        const double* __restrict__ cm = w.cum + nb;
-        const i32* __restrict__ cidx = w.csr_idx + 2 * w.cstart[g];
-        const u64 gidx = gbase + (u64)g;
-        const u64 kseed = seed_mode ? seed + gidx : seed;
-        const u64 cg = seed_mode ? 0ull : gidx;
-        const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
-        if (i == 0 && gi.level > 0) n_relaxed++;
-
-        const u32 ictr = (u32)i + ibase;  // Philox counter word 0: the sample's index in the WHOLE job
-        Philox4 r = philox4x32_10(ictr, 0u, c2, c3, k0, k1);
+// One sample of a general-path graph by one warp: root draw, growth on the two-level cut bitmap, induced-entry count.
+// Returns the sample size; lane j < size holds S[j] in `mine`; cntE = induced CSR entries (valid when size == k).
+__device__ __forceinline__ int sample_general_one(const u32* __restrict__ rp, const i32* __restrict__ cidx,
+                                                  const i32* __restrict__ iof, const i32* __restrict__ ord,
+                                                  const double* __restrict__ cm, const ugs_ginfo& gi, int n, int k, u32 ictr,
+                                                  u32 c2, u32 c3, u32 k0, u32 k1, u32* bm, u32* bc, int lane, int& mine,
+                                                  int& cntE_out) {
+    {
+                Philox4 r = philox4x32_10(ictr, 0u, c2, c3, k0, k1);
         const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
         int a = warp_cdf_search(cm, n, x, lane);
         if (gi.level == 0 && !(cm[a] > x)) a = gi.last_viable;
         const int root_vi = a;
 
-        int mine = -1;           // lane j holds S[j] ...
+        mine = -1;                 // lane j holds S[j] ...
         u32 my_p0 = 0, my_p1 = 0;  // ... and the bounds of its CSR row
         int size = 0;
         int cutn = 0;
@@ -442,7 +404,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
                     const u32 word_src = __shfl_sync(FULL_MASK, word, src);
                     xnew = (blk * 32 + src) * 32 + select_bit32(word_src, rsel - excl_src);
                 }
-                if (lane == 0) { bm[xnew >> 5] &= ~(1u << (xnew & 31)); bc[xnew >> 10] -= 1u; }
+                if (lane == 0) { bm[xnew >> 5] &= ~(1u << (xnew & 31)); if (nblk > 1) bc[xnew >> 10] -= 1u; }
                 cutn--;
                 __syncwarp();
             }
@@ -457,7 +419,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
                 if (iof[y] >= root_vi) {
                     const u32 bit = 1u << (y & 31);
                     const u32 old = atomicOr(&bm[y >> 5], bit);
-                    if (!(old & bit)) { atomicAdd(&bc[y >> 10], 1u); delta++; }
+                    if (!(old & bit)) { if (nblk > 1) atomicAdd(&bc[y >> 10], 1u); delta++; }
                 }
             }
             __syncwarp();
@@ -465,7 +427,7 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
             if (lane < size) {
                 const u32 bit = 1u << (mine & 31);
                 const u32 old = atomicAnd(&bm[mine >> 5], ~bit);
-                if (old & bit) { atomicSub(&bc[mine >> 10], 1u); delta--; }
+                if (old & bit) { if (nblk > 1) atomicSub(&bc[mine >> 10], 1u); delta--; }
             }
             cutn += __reduce_add_sync(FULL_MASK, delta);
             __syncwarp();
@@ -504,19 +466,220 @@ k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 s
             if (lane < size) atomicAnd(&bm[mine >> 5], ~(1u << (mine & 31)));
             __syncwarp();
         }
-        const i64 sidx = g * m + i;
-        if (lane < k) nodes_out[sidx * k + lane] = (lane < size) ? lo + (i64)mine : (i64)-1;
-        if (lane == 0) {
-            edge_ptr[1 + sidx] = (size == k) ? (i64)cntE : 0;
-            if (size < k) n_incomplete++;
-            else n_entries += (unsigned long long)cntE;
-        }
+        cntE_out = cntE;
+        return size;
     }
+}
+
+#ifndef MEDS_THREADS
+#define MEDS_THREADS 128  // k_sample_medium: samples (threads) per CTA
+#endif
+#ifndef MEDS_MIN_SAMPLES
+#define MEDS_MIN_SAMPLES 10000  // general-path samples of a batch from which k_sample_medium takes the PROTEINS-sized graphs
+#endif
+#ifndef GEN_MINB
+#define GEN_MINB 5  // resident CTAs per SM the kernel is compiled for (51 registers -> 40 warps per SM)
+#endif
+// PROTEINS-sized general-path graphs (ugs_is_medium: <= 1024 vertices, <= 3072 columns) are sampled by k_sample_medium
+// with their tables in shared memory; this kernel takes the rest.
+
+__global__ void __launch_bounds__(256, GEN_MINB)
+k_sample_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
+                 int seed_mode, i64 n_general, int bm_words, int bm_stride, WS w,
+                 i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr) {
+    extern __shared__ __align__(16) u32 bm_all[];
+    if (n_general < 0) n_general = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
+    if (n_general == 0) return;
+    // a batch with many general-path samples: PROTEINS-sized graphs belong to k_sample_medium (see there)
+    const bool skip_medium = n_general * m >= MEDS_MIN_SAMPLES;
+    if (skip_medium && w.counters[UGS_CTR_N_NOT_MEDIUM] == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32* bm = bm_all + (size_t)warp * bm_stride;  // [bm_words] cut bitmap (bm_words is a multiple of 32)
+    u32* bc = bm + bm_words;                      // [bm_words / 32] set bits per block of 32 words
+    for (int i = lane; i < bm_stride; i += 32) bm[i] = 0;
+    __syncwarp();
+    const i64 total = n_general * m;
+    unsigned long long n_incomplete = 0, n_relaxed = 0, n_entries = 0;
+
+    // a claim covers GEN_WORK_CHUNK samples when there is plenty of work, one sample when every warp gets only a few
+    const int chunk = (total >= (i64)gridDim.x * (blockDim.x >> 5) * (2 * GEN_WORK_CHUNK)) ? GEN_WORK_CHUNK : 1;
+    while (true) {
+        i64 tbase = 0;
+        if (lane == 0) tbase = (i64)atomicAdd(&w.counters[UGS_CTR_WORK], (unsigned long long)chunk);
+        tbase = __shfl_sync(FULL_MASK, tbase, 0);
+        if (tbase >= total) break;
+        const i64 tend = min(total, tbase + chunk);
+        for (i64 t = tbase; t < tend; ++t) {
+            const i64 gi_ = t / m;
+            const i64 i = t - gi_ * m;
+            const i64 g = w.glist[gi_];
+            const i64 lo = ptr[g];
+            const int n = (int)(ptr[g + 1] - lo);
+            if (skip_medium && ugs_is_medium(n, w.cstart[g + 1] - w.cstart[g])) continue;  // k_sample_medium
+            const ugs_ginfo gi = w.ginfo[g];
+            const i64 nb = lo - node_base;
+            const u64 gidx = gbase + (u64)g;
+            const u64 kseed = seed_mode ? seed + gidx : seed;
+            const u64 cg = seed_mode ? 0ull : gidx;
+            if (i == 0 && gi.level > 0) n_relaxed++;
+            int mine = -1, cntE = 0;
+            const int size = sample_general_one(w.rowptr + nb + g, w.csr_idx + 2 * w.cstart[g], w.index_of + nb, w.order + nb,
+                                                w.cum + nb, gi, n, k, (u32)i + ibase, (u32)cg, (u32)(cg >> 32), (u32)kseed,
+                                                (u32)(kseed >> 32), bm, bc, lane, mine, cntE);
+            const i64 sidx = g * m + i;
+            if (lane < k) nodes_out[sidx * k + lane] = (lane < size) ? lo + (i64)mine : (i64)-1;
+            if (lane == 0) {
+                edge_ptr[1 + sidx] = (size == k) ? (i64)cntE : 0;
+                if (size < k) n_incomplete++;
+                else n_entries += (unsigned long long)cntE;
+            }
+        }
     }
     if (lane == 0) {
         if (n_entries) atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], n_entries);
         if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], n_incomplete);
         if (n_relaxed) atomicAdd(&w.counters[UGS_CTR_RELAXED], n_relaxed);
+    }
+}
+
+// PROTEINS-sized general-path graphs (ugs_is_medium) of a batch with at least MEDS_MIN_SAMPLES general-path samples: one
+// THREAD per sample, one CTA per (graph, blockDim.x samples). The CTA stages the graph's row pointers, neighbour ids,
+// order positions, order and root CDF in shared memory once (<= 44 KB, by asynchronous copies that are all in flight
+// together); every thread keeps its cut and its member set as bitmaps of ceil(n / 32) words in shared memory, word w of
+// thread t at [w * blockDim.x + t] (always bank t % 32: conflict-free whatever words the threads of a warp touch). A
+// growth step is a popcount walk over the words to the r-th set bit and one walk over the new member's row, 32 samples
+// per instruction, where the warp-per-sample kernel spends ~300 instructions per sample and step on scans, votes and
+// shuffles: 34 M warp instructions for the 17 000 general-path samples of a 1113-graph PROTEINS batch, issue-bound at
+// 54 us. The price is latency -- one thread walks the whole chain of a sample, ~25 us whatever the batch -- which is why
+// small batches stay with k_sample_general.
+struct __align__(16) MedSample {
+    double cum[1024];
+    i32 idx[6144];
+    u32 rowptr[1028];  // 1025 used
+    i32 iof[1024];
+    i32 ord[1024];
+};
+
+__global__ void __launch_bounds__(MEDS_THREADS)
+k_sample_medium(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
+                int seed_mode, i64 n_general, i64 chunks_per_graph, WS w, i64* __restrict__ nodes_out,
+                i64* __restrict__ edge_ptr) {
+    extern __shared__ __align__(16) unsigned char meds_raw[];
+    MedSample& s = *reinterpret_cast<MedSample*>(meds_raw);
+    const int T = blockDim.x;
+    u32* bm = reinterpret_cast<u32*>(meds_raw + sizeof(MedSample)) + threadIdx.x;  // cut, word w of this thread: bm[w * T]
+    u32* ms = bm + 32 * T;                                                         // members of S, same layout
+    if (n_general < 0) n_general = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
+    if (n_general * m < MEDS_MIN_SAMPLES) return;  // few samples: k_sample_general, a warp per sample, is the faster one
+    int n_incomplete = 0, n_relaxed = 0;
+    unsigned long long n_entries = 0;
+    for (i64 item = blockIdx.x; item < n_general * chunks_per_graph; item += gridDim.x) {
+        const i64 gi_ = item / chunks_per_graph;
+        const i64 c = item - gi_ * chunks_per_graph;
+        const i64 g = w.glist[gi_];
+        const i64 lo = ptr[g];
+        const int n = (int)(ptr[g + 1] - lo);
+        const i64 c0 = w.cstart[g];
+        if (!ugs_is_medium(n, w.cstart[g + 1] - c0)) continue;  // k_sample_general
+        const ugs_ginfo gi = w.ginfo[g];
+        const i64 nb = lo - node_base;
+        __syncthreads();  // the previous item's samples are done with the tables
+        {
+            const u32* rp = w.rowptr + nb + g;
+            const i32* ci = w.csr_idx + 2 * c0;  // 8-byte aligned, nnz = 2 * columns
+            for (int v = threadIdx.x; v <= n; v += T) cp_async_4(&s.rowptr[v], rp + v);
+            for (int v = threadIdx.x; v < n; v += T) {
+                cp_async_8(&s.cum[v], w.cum + nb + v);
+                cp_async_4(&s.iof[v], w.index_of + nb + v);
+                cp_async_4(&s.ord[v], w.order + nb + v);
+            }
+            for (int p = threadIdx.x; 2 * p < gi.nnz; p += T) cp_async_8(&s.idx[2 * p], ci + 2 * p);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        if (c == 0 && threadIdx.x == 0 && gi.level > 0) n_relaxed++;
+        const i64 i = c * T + threadIdx.x;
+        if (i >= m) continue;
+        const u64 gidx = gbase + (u64)g;
+        const u64 kseed = seed_mode ? seed + gidx : seed;
+        const u64 cg = seed_mode ? 0ull : gidx;
+        const u32 ictr = (u32)i + ibase, c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
+        const int words = (n + 31) >> 5;
+        for (int q = 0; q < words; ++q) { bm[q * T] = 0u; ms[q * T] = 0u; }
+
+        Philox4 r = philox4x32_10(ictr, 0u, c2, c3, k0, k1);
+        const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
+        int root_vi;
+        {   // first position with cum > x (n - 1 when there is none), as warp_cdf_search
+            int a = 0, b = n;
+            while (a < b) { const int mid = (a + b) >> 1; if (s.cum[mid] > x) b = mid; else a = mid + 1; }
+            if (a >= n) a = n - 1;
+            if (gi.level == 0 && !(s.cum[a] > x)) a = gi.last_viable;
+            root_vi = a;
+        }
+        unsigned short S[UGS_MAX_K];
+        int size = 0, cutn = 0;
+        int pairs = 0, selfs = 0;  // row entries that point at an EARLIER member / at the member itself
+        int xnew = s.ord[root_vi];
+        for (int step = 0; step < k; ++step) {
+            if (step > 0) {
+                if (cutn == 0) break;
+                const int wsel = (step + 1) & 3;
+                if (wsel == 0) r = philox4x32_10(ictr, (u32)((step + 1) >> 2), c2, c3, k0, k1);
+                const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
+                int rsel = (int)__umulhi(wv, (u32)cutn);
+                int q = 0;
+                u32 word = 0u;
+                for (; q < words; ++q) {  // the r-th set bit in ascending vertex id
+                    word = bm[q * T];
+                    const int pc = __popc(word);
+                    if (rsel < pc) break;
+                    rsel -= pc;
+                }
+                if (q >= words) break;  // cannot happen: cutn is the number of set bits
+                const int bit = select_bit32(word, rsel);
+                bm[q * T] = word & ~(1u << bit);
+                xnew = q * 32 + bit;
+                cutn--;
+            }
+            S[size++] = (unsigned short)xnew;
+            ms[(xnew >> 5) * T] |= 1u << (xnew & 31);
+            // One walk over row(xnew) does both jobs: entries that point into S are counted (see below), the other
+            // suffix vertices (index_of >= root position) join the cut -- except after the last member, whose row
+            // cannot extend the sample any more.
+            const bool grow = step < k - 1;
+            for (u32 p = s.rowptr[xnew], p1 = s.rowptr[xnew + 1]; p < p1; ++p) {
+                const int y = s.idx[p];
+                const u32 bit = 1u << (y & 31);
+                if (ms[(y >> 5) * T] & bit) {
+                    if (y == xnew) selfs++; else pairs++;
+                } else if (grow && s.iof[y] >= root_vi) {
+                    const u32 old = bm[(y >> 5) * T];
+                    if (!(old & bit)) { bm[(y >> 5) * T] = old | bit; cutn++; }
+                }
+            }
+        }
+        // Induced CSR entries. Every column is stored in both directions, so u appears in row(v) as often as v in row(u):
+        // the entries between two members are twice those seen from the LATER member's row at the moment it joined.
+        int cntE = 0;
+        if (size == k) {
+            cntE = 2 * pairs + selfs;
+            n_entries += (unsigned long long)cntE;
+        } else {
+            n_incomplete++;
+        }
+        const i64 sidx = g * m + i;
+        for (int j = 0; j < k; ++j) nodes_out[sidx * k + j] = (j < size) ? lo + (i64)S[j] : (i64)-1;
+        edge_ptr[1 + sidx] = (i64)cntE;
+    }
+    // per-warp totals (a thread's entries fit 32 bits: at most 2 * 3072 * k per sample, few samples per thread)
+    const u32 e32 = __reduce_add_sync(FULL_MASK, (u32)n_entries);
+    const int inc = __reduce_add_sync(FULL_MASK, n_incomplete);
+    const int rel = __reduce_add_sync(FULL_MASK, n_relaxed);
+    if ((threadIdx.x & 31) == 0) {
+        if (e32) atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], (unsigned long long)e32);
+        if (inc) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)inc);
+        if (rel) atomicAdd(&w.counters[UGS_CTR_RELAXED], (unsigned long long)rel);
     }
 }
 
@@ -906,7 +1069,9 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-             i64* __restrict__ out_src, const u64* __restrict__ packed) {
+             i64* __restrict__ out_src, const u64* __restrict__ packed, int check_general) {
+    // fused path queued on the guess "no general-path graph": a wrong guess leaves garbage offsets, write nothing then
+    if (check_general && w.counters[UGS_CTR_N_GENERAL] != 0) return;
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
@@ -939,7 +1104,8 @@ template <int S>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 4)
 k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, WS w,
                     const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr, i64* __restrict__ out_u,
-                    i64* __restrict__ out_v, i64* __restrict__ out_src, const u64* __restrict__ packed) {
+                    i64* __restrict__ out_v, i64* __restrict__ out_src, const u64* __restrict__ packed, int check_general) {
+    if (check_general && w.counters[UGS_CTR_N_GENERAL] != 0) return;  // see k_emit_small
     constexpr int GPW = 32 / S;
     constexpr size_t SLICE = sizeof(PackedEmit<GPW>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<GPW>)
                                                                                             : sizeof(SmallEmit<unsigned short>);
@@ -1355,7 +1521,21 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
         UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_general, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             cudaSharedmemCarveoutMaxShared));
         UGS_CUDA_CHECK(cudaMemsetAsync(&w.counters[UGS_CTR_WORK], 0, sizeof(i64), st));
-        const int64_t total = (n_general < 0 ? G : n_general) * m;
+        const int64_t ngb = n_general < 0 ? G : n_general;  // (bound on) the number of general-path graphs
+        // PROTEINS-sized graphs of a batch with many general-path samples: tables in shared memory, one thread per sample
+        if (ngb * m >= MEDS_MIN_SAMPLES) {
+            const int mthreads = (int)(m >= MEDS_THREADS ? MEDS_THREADS : ((m + 31) / 32) * 32);
+            const int64_t cpg = (m + mthreads - 1) / mthreads;
+            const size_t msmem = sizeof(MedSample) + (size_t)64 * mthreads * sizeof(u32);
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_medium, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            int64_t mblocks = ngb * cpg;
+            const int64_t mcap = (int64_t)sm_count() * 16;
+            if (mblocks > mcap) mblocks = mcap;
+            k_sample_medium<<<(unsigned)mblocks, mthreads, msmem, st>>>(ptr, G, node_base, m, k, seed, graph_index_base, ibase,
+                                                                       seed_mode, n_general, cpg, w, nodes, edge_ptr);
+            UGS_LAUNCH_CHECK("k_sample_medium");
+        }
+        const int64_t total = ngb * m;
         int64_t blocks = (total + wpb - 1) / wpb;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
@@ -1415,6 +1595,10 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
     WS w = ws_views(const_cast<void*>(workspace), L);
     i64* out_u = edge_index_out;
     i64* out_v = edge_index_out + total;
+    // n_general == -2 (ugs_sample_batch_fused with assume_no_general): no general-path launch, and the bitmask-path
+    // kernels write nothing when the device count says there was such a graph after all
+    const int guard = (n_general == -2) ? 1 : 0;
+    if (guard) n_general = 0;
     const u64* packed = nullptr;  // rows as ugs_sample_batch packed them for exactly these (G, m, k <= 8)
     if (sample_scratch && k <= 8 && sample_scratch_bytes >= ugs_sample_scratch_bytes(G, m))
         packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
@@ -1432,28 +1616,29 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
                 const size_t sl = sizeof(PackedEmit<4>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<4>) : sizeof(SmallEmit<unsigned short>);
                 UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
                 k_emit_small_packed<8><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
-                                                                                       out_u, out_v, edge_src_out, packed);
+                                                                                       out_u, out_v, edge_src_out, packed, guard);
             } else {
                 const size_t sl = sizeof(PackedEmit<2>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<2>) : sizeof(SmallEmit<unsigned short>);
                 UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
                 k_emit_small_packed<16><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
-                                                                                        out_u, out_v, edge_src_out, packed);
+                                                                                        out_u, out_v, edge_src_out, packed, guard);
             }
         } else if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
             const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out, packed);
+                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out, packed, guard);
         } else {
             const size_t smem = sizeof(SmallEmit<u32>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<false><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out, nullptr);
+                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out, nullptr, guard);
         }
         UGS_LAUNCH_CHECK("k_emit_small");
     }
     if (n_general != 0) {
-        int64_t blocks = ((n_general < 0 ? G : n_general) * m + 7) / 8;
+        const int64_t ngb = n_general < 0 ? G : n_general;
+        int64_t blocks = (ngb * m + 7) / 8;
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         k_emit_general<false><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, mode, n_general, true, w, nodes,

@@ -137,7 +137,7 @@ def lib():
     L.ugs_fused_capacity.restype = i64
     L.ugs_fused_capacity.argtypes = [i64, i64]
     L.ugs_sample_batch_fused.argtypes = [vp, i64, vp, i64, i64, i64, i64, ci, ci, u64, u64, u64, ci, vp, LP, vp, sz,
-                                         vp, vp, vp, vp, vp, vp, i64, vp, vp]
+                                         vp, vp, vp, vp, vp, vp, i64, vp, ci, vp]
     L.ugs_fused_finish.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.ugs_deliver_wire_bytes.restype = sz
     L.ugs_deliver_wire_bytes.argtypes = [i64, ci, i64, ci]

@@ -510,16 +510,25 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
             hi = slots[dev.index] = (t, t.numpy())
         base = tmp.data_ptr()
         stream = torch.cuda.current_stream().cuda_stream
-        rc = L.ugs_sample_batch_fused(
-            edge_index.data_ptr(), E, ptr.data_ptr(), G, int(node_base), NT, m, k, MODES[mode], seed & (2 ** 64 - 1),
-            int(graph_index_base), int(sample_index_base), 1 if per_graph_seed else 0, base, ctypes.byref(lay),
-            base + off_s, sbytes, nodes.data_ptr(), edge_ptr.data_ptr(), sample_ptr.data_ptr(), base + off_e,
-            base + off_e + 8 * cap, base + off_e + 16 * cap, cap, hi[0].data_ptr(), stream)
-        if rc != 0:
-            _lib.check(rc)
-        info = hi[1]
-        if info[CTR["unsorted"]]:
-            return None
+        # Batches of one data set look alike: after a batch without general-path graphs (every MUTAG / QM9 / ZINC batch)
+        # the next one is queued without the general-path kernels, and repeated with them if the device count says the
+        # guess was wrong (the outputs of the first attempt are void then).
+        guess = 1 if (slots.get(("no_general", dev.index)) and k <= 16) else 0
+        while True:
+            rc = L.ugs_sample_batch_fused(
+                edge_index.data_ptr(), E, ptr.data_ptr(), G, int(node_base), NT, m, k, MODES[mode], seed & (2 ** 64 - 1),
+                int(graph_index_base), int(sample_index_base), 1 if per_graph_seed else 0, base, ctypes.byref(lay),
+                base + off_s, sbytes, nodes.data_ptr(), edge_ptr.data_ptr(), sample_ptr.data_ptr(), base + off_e,
+                base + off_e + 8 * cap, base + off_e + 16 * cap, cap, hi[0].data_ptr(), guess, stream)
+            if rc != 0:
+                _lib.check(rc)
+            info = hi[1]
+            if info[CTR["unsorted"]]:
+                return None
+            no_general = slots[("no_general", dev.index)] = int(info[CTR["n_general"]]) == 0
+            if not guess or no_general:
+                break
+            guess = 0
         total = int(info[CTR["total_edges"]])
         n_skipped = int(info[CTR["n_skipped"]])
         stats = dict(n_graphlets=B, n_edge_entries=total, n_incomplete=int(info[CTR["incomplete"]]),

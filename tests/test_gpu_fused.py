@@ -95,3 +95,23 @@ def test_dropin_takes_the_fused_path_for_minibatches(cuda_lib, monkeypatch):
     for x, y, r in zip(a, b, ref):
         assert not x.is_cuda and x.is_pinned() and torch.equal(x, y) and np.array_equal(x.numpy(), r)
     assert n1 - n0 >= 5 and n2 - n1 >= 5
+
+
+def test_fused_guess_without_general_path_graphs_is_checked(cuda_lib):
+    """After a batch without general-path graphs the next fused call is queued without the general-path kernels
+    (assume_no_general); when that batch does hold a graph above 64 vertices the device count exposes the wrong guess and
+    the call is repeated in full -- results stay bit-identical to the staged path in every order of batches."""
+    from ugs_b200 import synth
+    from ugs_b200.engine import _fused_tls
+    small = synth.make_batch("mutag", 40, seed=3)
+    mixed = synth.make_batch("proteins", 40, seed=3)
+    assert np.diff(mixed[1]).max() > 64 and np.diff(small[1]).max() <= 64
+    dev = torch.cuda.current_device()
+    for order in ([small, small, mixed, mixed, small], [mixed, small, mixed]):
+        for ei, ptr in order:
+            fo, fs = _fused(ei, ptr, 12, 5, "sample", 9)
+            so, ss = _staged(ei, ptr, 12, 5, "sample", 9)
+            for name, a, b in zip(NAMES, fo, so):
+                assert torch.equal(a, b), name
+            assert fs == ss
+            assert _fused_tls.info[("no_general", dev)] == (ss["n_general_graphs"] == 0)

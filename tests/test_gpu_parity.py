@@ -341,3 +341,26 @@ def test_small_m_packs_several_graphs_per_warp(cuda_lib, m, k):
         counts = (p_s[1:] - p_s[:-1])
         off = torch.repeat_interleave(torch.arange(n_s.shape[0], device=e_s.device), counts) * k
         assert torch.equal(e_e, e_s + off.unsqueeze(0)) and torch.equal(s_e, s_s) and torch.equal(p_e, p_s)
+
+
+@pytest.mark.parametrize("k,m", [(6, 640), (3, 700), (12, 800)])
+def test_many_general_path_samples_take_the_thread_per_sample_kernel(cuda_lib, k, m):
+    """A batch with >= 10 000 general-path samples hands its PROTEINS-sized graphs (<= 1024 vertices, <= 3072 columns) to
+    k_sample_medium (one thread per sample, tables in shared memory, induced entries counted by symmetry during the
+    growth) and leaves the larger ones with the warp-per-sample kernel: same bits as the oracle either way. The graphs
+    carry self loops, duplicate and one-direction columns, and sizes at the kernel's limits."""
+    rng = np.random.default_rng(1000 + k)
+    sizes = [65, 100, 333, 700, 1023, 1024, 1025, 1500, 90, 256]
+    ei, ptr = random_batch(rng, 64, 1, 60, deg=1.4, weird=True, big=[(3 * i + 1, s_) for i, s_ in enumerate(sizes)])
+    ei2, ptr2 = random_batch(rng, 3, 800, 1000, deg=3.5, weird=True)  # more than 3072 columns: not "medium"
+    from ugs_b200 import synth
+    ei, ptr = synth.concat_batches([(ei, ptr), (ei2, ptr2), synth.make_batch("proteins", 30, seed=k)])
+    b = _batch(ei, ptr, k)
+    assert b.n_general * m >= 10000
+    for mode in ("sample", "global"):
+        outs, stats = b.sample(m, k, mode, seed=3)
+        ref = _oracle_batch(ei, ptr, m, k, mode, 3)
+        for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+            assert np.array_equal(a.cpu().numpy(), r), (name, mode)
+        assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
+        assert stats["n_edge_entries"] == ref[1].shape[1]
