@@ -239,22 +239,33 @@ int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m,
  * host round trips, not kernel time. ugs_sample_batch_fused queues segment -> preprocess -> sample -> scan -> emit
  * back to back (UGS_VARIANT_REF, graph-contiguous columns): the general-path kernels get worst-case grids and read
  * their item counts from counters[] on the device, and the emission pass writes into ei_u / ei_v (= ei_u + cap) /
- * ei_src of cap >= ugs_fused_capacity(E, m) = 2*E*m entries (a sample emits every CSR entry at most once). The stream
- * is synchronised once, after counters[] has been copied to h_info (pinned host memory, UGS_CTR_COUNT int64):
+ * ei_src of cap >= ugs_fused_capacity(E, m) = 2*E*m entries (a sample emits every CSR entry at most once). The only
+ * thing the host waits for is counters[] in h_info (pinned host memory, UGS_CTR_COUNT int64; word UGS_CTR_COUNT-1 is
+ * used as the arrival flag): the scan kernel writes them through the mapped address as soon as the total is known and
+ * the call returns when they have arrived -- the emission kernels may still be running, the outputs are valid in STREAM
+ * order (the next kernel or copy on `stream` sees them; a host read needs a stream synchronisation first). When h_info
+ * is not device-mapped the counters are copied back after the emission and the stream is synchronised instead.
  * h_info[UGS_CTR_TOTAL_EDGES] = Ebar; a non-zero h_info[UGS_CTR_UNSORTED] means the batch needs the staged path and no
  * output is valid. ugs_fused_finish narrows the bound-sized arrays into edge_index_out[2,Ebar] / edge_src_out[Ebar].
  * Outputs are bit-identical to the staged sequence.
- * assume_no_general != 0 leaves the general-path kernels out of the queue (five launches that would return at once --
- * ~3 us each in a 0.1 ms chain -- when the batch has no graph above 64 nodes / 384 columns, as every MUTAG / QM9 / ZINC
- * batch): the caller must then check h_info[UGS_CTR_N_GENERAL]; non-zero voids the outputs and the call has to be
- * repeated with assume_no_general = 0. */
+ * flags:
+ *   UGS_FUSED_ASSUME_NO_GENERAL leaves the general-path kernels out of the queue (five launches that would return at
+ *     once -- ~3 us each in a 0.1 ms chain -- when the batch has no graph above 64 nodes / 384 columns, as every MUTAG /
+ *     QM9 / ZINC batch): the caller must then check h_info[UGS_CTR_N_GENERAL]; non-zero voids the outputs and the call
+ *     has to be repeated without the flag.
+ *   UGS_FUSED_COMPACT makes the emission kernels read Ebar on the device and write the three rows behind one another:
+ *     ei_u[0, Ebar) | [Ebar, 2 Ebar) | [2 Ebar, 3 Ebar) of ONE array of 3*cap entries (ei_v = ei_u + cap and
+ *     ei_src = ei_v + cap on entry). The first 3*Ebar entries then ARE edge_index[2,Ebar] and edge_src[Ebar]; no
+ *     ugs_fused_finish pass. For callers who can live with results that are views of the bound-sized allocation. */
+#define UGS_FUSED_ASSUME_NO_GENERAL 1
+#define UGS_FUSED_COMPACT 2
 int64_t ugs_fused_capacity(int64_t E, int64_t m);
 int ugs_sample_batch_fused(const int64_t* edge_index, int64_t E, const int64_t* ptr, int64_t G, int64_t node_base,
                            int64_t total_nodes, int64_t m, int k, int mode, uint64_t seed, uint64_t graph_index_base,
                            uint64_t sample_index_base, int seed_mode, void* workspace, const ugs_layout* L,
                            void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr, int64_t* sample_ptr,
-                           int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info,
-                           int assume_no_general, void* stream);
+                           int64_t* ei_u, int64_t* ei_v, int64_t* ei_src, int64_t cap, int64_t* h_info, int flags,
+                           void* stream);
 int ugs_fused_finish(const int64_t* ei_u, const int64_t* ei_v, const int64_t* ei_src, int64_t total,
                      int64_t* edge_index_out, int64_t* edge_src_out, void* stream);
 

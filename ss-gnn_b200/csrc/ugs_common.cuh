@@ -173,8 +173,15 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __host__ __device__ __forceinline__ bool ugs_is_medium(long long n, long long nc) { return n <= 1024 && nc <= 3072; }
 
 // internal entry points shared between translation units
+#define UGS_EMIT_GUARD_GENERAL 1  // write nothing when counters[UGS_CTR_N_GENERAL] != 0 (fused path queued on a guess)
+#define UGS_EMIT_COMPACT 2        // out_v / out_src follow out_u at counters[UGS_CTR_TOTAL_EDGES] (read on the device)
+int ugs_emit_edges_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode, int use_perm,
+                        int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                        const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                        const void* sample_scratch, size_t sample_scratch_bytes, int flags, void* stream_);
 int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, uint64_t seed,
                           uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
                           int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
                           void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
-                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh);
+                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh,
+                          int64_t* snap = nullptr, int64_t snap_seq = 0);  // snap: see k_scan_counts

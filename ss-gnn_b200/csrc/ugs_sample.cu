@@ -699,7 +699,7 @@ k_sample_medium(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k,
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ scratch,
-              unsigned long long* __restrict__ counters) {
+              unsigned long long* __restrict__ counters, volatile i64* snap, i64 snap_seq) {
     // Coalesced global access (a warp reads 32 consecutive counts per instruction), transposed through a padded
     // shared tile so that every thread scans SCAN_ITEMS consecutive counts in registers.
     __shared__ i64 s_tile_[SCAN_THREADS / 32][32 * (SCAN_ITEMS + 1)];
@@ -769,6 +769,19 @@ k_scan_counts(i64* __restrict__ data, i64 B, unsigned long long* __restrict__ sc
         if (lane == 0) {
             s_prefix = prefix;
             if ((tile + 1) * SCAN_TILE >= B) counters[UGS_CTR_TOTAL_EDGES] = (unsigned long long)(prefix + block_total);
+        }
+        // Fused small-batch path: everything the host waits for (total, class counts, flags, statistics) is final here,
+        // so the last tile writes counters[] straight into mapped host memory, sequence word last: the host polls that
+        // word and never synchronises with the emission kernels behind this one.
+        if (snap && (tile + 1) * SCAN_TILE >= B) {
+            for (int q = lane; q < UGS_CTR_COUNT - 1; q += 32)
+                snap[q] = (q == UGS_CTR_TOTAL_EDGES) ? (prefix + block_total) : (i64)counters[q];
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();
+                snap[UGS_CTR_COUNT - 1] = snap_seq;
+            }
         }
     }
     __syncthreads();
@@ -1069,9 +1082,14 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-             i64* __restrict__ out_src, const u64* __restrict__ packed, int check_general) {
+             i64* __restrict__ out_src, const u64* __restrict__ packed, int flags) {
     // fused path queued on the guess "no general-path graph": a wrong guess leaves garbage offsets, write nothing then
-    if (check_general && w.counters[UGS_CTR_N_GENERAL] != 0) return;
+    if ((flags & UGS_EMIT_GUARD_GENERAL) && w.counters[UGS_CTR_N_GENERAL] != 0) return;
+    if (flags & UGS_EMIT_COMPACT) {  // rows packed behind one another at the total the scan kernel left on the device
+        const i64 t = (i64)w.counters[UGS_CTR_TOTAL_EDGES];
+        out_v = out_u + t;
+        out_src = out_u + 2 * t;
+    }
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     SmallEmit<stage_t>* sm_all = reinterpret_cast<SmallEmit<stage_t>*>(emit_smem_raw);
@@ -1104,8 +1122,13 @@ template <int S>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 4)
 k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, WS w,
                     const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr, i64* __restrict__ out_u,
-                    i64* __restrict__ out_v, i64* __restrict__ out_src, const u64* __restrict__ packed, int check_general) {
-    if (check_general && w.counters[UGS_CTR_N_GENERAL] != 0) return;  // see k_emit_small
+                    i64* __restrict__ out_v, i64* __restrict__ out_src, const u64* __restrict__ packed, int flags) {
+    if ((flags & UGS_EMIT_GUARD_GENERAL) && w.counters[UGS_CTR_N_GENERAL] != 0) return;  // see k_emit_small
+    if (flags & UGS_EMIT_COMPACT) {
+        const i64 t = (i64)w.counters[UGS_CTR_TOTAL_EDGES];
+        out_v = out_u + t;
+        out_src = out_u + 2 * t;
+    }
     constexpr int GPW = 32 / S;
     constexpr size_t SLICE = sizeof(PackedEmit<GPW>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<GPW>)
                                                                                             : sizeof(SmallEmit<unsigned short>);
@@ -1252,10 +1275,15 @@ template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(256)
 k_emit_general(const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mode, i64 n_items, bool use_glist,
                WS w, const i64* __restrict__ nodes, i64* __restrict__ edge_ptr, i64 total,
-               i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src) {
+               i64* __restrict__ out_u, i64* __restrict__ out_v, i64* __restrict__ out_src, int flags) {
     __shared__ __align__(16) unsigned char pos_all[8][1024];
     if (n_items < 0) n_items = (i64)w.counters[UGS_CTR_N_GENERAL];  // fused small-batch path
     if (n_items == 0) return;
+    if (!COUNT_ONLY && (flags & UGS_EMIT_COMPACT)) {  // see k_emit_small
+        total = (i64)w.counters[UGS_CTR_TOTAL_EDGES];
+        out_v = out_u + total;
+        out_src = out_u + 2 * total;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     unsigned char* pos = pos_all[warp];
     {
@@ -1357,13 +1385,15 @@ extern "C" size_t ugs_sample_scratch_bytes(int64_t G, int64_t m) {
     return packed_rows_offset(B) + (size_t)B * sizeof(u64);
 }
 
-static int run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& w, cudaStream_t st) {
+static int run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& w, cudaStream_t st,
+                    i64* snap = nullptr, i64 snap_seq = 0) {
     const size_t need = scan_scratch_bytes(B);
     if (scratch_bytes < need || !scratch) return ugs_set_error(UGS_EINVAL, "scratch too small: %zu < %zu", scratch_bytes, need);
     UGS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, need, st));
     if (B > 0) {
         const i64 tiles = (B + SCAN_TILE - 1) / SCAN_TILE;
-        k_scan_counts<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(edge_ptr + 1, B, (unsigned long long*)scratch, w.counters);
+        k_scan_counts<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(edge_ptr + 1, B, (unsigned long long*)scratch, w.counters, snap,
+                                                                snap_seq);
         UGS_LAUNCH_CHECK("k_scan_counts");
     }
     return UGS_OK;
@@ -1412,7 +1442,8 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
                           uint64_t graph_index_base, uint64_t sample_index_base, int seed_mode, int variant,
                           int64_t n_general, int64_t max_n_general, void* workspace, const ugs_layout* L,
                           void* scratch, size_t scratch_bytes, int64_t* nodes, int64_t* edge_ptr,
-                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh) {
+                          int64_t* sample_ptr, int64_t* h_info, void* stream_, bool counters_fresh, int64_t* snap,
+                          int64_t snap_seq) {
     if (!workspace || !L || !edge_ptr || !sample_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (h_info && variant != UGS_VARIANT_REF) return ugs_set_error(UGS_EINVAL, "the early read-back needs UGS_VARIANT_REF");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
@@ -1548,7 +1579,7 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
         const int rc = ugs_batch_info_begin(workspace, L, h_info, stream_);
         if (rc != UGS_OK) return rc;
     }
-    return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
+    return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st, snap, snap_seq);
 }
 
 extern "C" int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
@@ -1567,7 +1598,7 @@ extern "C" int ugs_count_edges(const int64_t* ptr, int64_t G, int64_t node_base,
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     k_emit_general<true><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, 0, G, false, w, nodes, edge_ptr, 0,
-                                                          nullptr, nullptr, nullptr);
+                                                          nullptr, nullptr, nullptr, 0);
     UGS_LAUNCH_CHECK("k_count_general");
     (void)n_general;
     return run_scan(edge_ptr, G * m, scratch, scratch_bytes, w, st);
@@ -1586,6 +1617,15 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
                                      const int64_t* nodes, const int64_t* edge_ptr, int64_t total,
                                      int64_t* edge_index_out, int64_t* edge_src_out, const void* sample_scratch,
                                      size_t sample_scratch_bytes, void* stream_) {
+    return ugs_emit_edges_impl(ptr, G, node_base, m, k, mode, use_perm, n_general, workspace, L, nodes, edge_ptr, total,
+                               edge_index_out, edge_src_out, sample_scratch, sample_scratch_bytes, 0, stream_);
+}
+
+// flags: UGS_EMIT_GUARD_GENERAL / UGS_EMIT_COMPACT (ugs_common.cuh), set by the fused small-batch path only
+int ugs_emit_edges_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int mode, int use_perm,
+                        int64_t n_general, const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                        const int64_t* edge_ptr, int64_t total, int64_t* edge_index_out, int64_t* edge_src_out,
+                        const void* sample_scratch, size_t sample_scratch_bytes, int flags, void* stream_) {
     if (!workspace || !L || !edge_ptr) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (mode < 0 || mode > UGS_MODE_ENCODER) return ugs_set_error(UGS_EINVAL, "mode must be one of: 'sample', 'graph', 'global'");
     if (k < 1 || k > UGS_MAX_K) return ugs_set_error(UGS_ELIMIT, "k must be in [1, %d]", UGS_MAX_K);
@@ -1595,10 +1635,9 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
     WS w = ws_views(const_cast<void*>(workspace), L);
     i64* out_u = edge_index_out;
     i64* out_v = edge_index_out + total;
-    // n_general == -2 (ugs_sample_batch_fused with assume_no_general): no general-path launch, and the bitmask-path
-    // kernels write nothing when the device count says there was such a graph after all
-    const int guard = (n_general == -2) ? 1 : 0;
-    if (guard) n_general = 0;
+    // UGS_EMIT_GUARD_GENERAL (ugs_sample_batch_fused with assume_no_general): no general-path launch, and the
+    // bitmask-path kernels write nothing when the device count says there was such a graph after all
+    if (flags & UGS_EMIT_GUARD_GENERAL) n_general = 0;
     const u64* packed = nullptr;  // rows as ugs_sample_batch packed them for exactly these (G, m, k <= 8)
     if (sample_scratch && k <= 8 && sample_scratch_bytes >= ugs_sample_scratch_bytes(G, m))
         packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
@@ -1616,23 +1655,23 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
                 const size_t sl = sizeof(PackedEmit<4>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<4>) : sizeof(SmallEmit<unsigned short>);
                 UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
                 k_emit_small_packed<8><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
-                                                                                       out_u, out_v, edge_src_out, packed, guard);
+                                                                                       out_u, out_v, edge_src_out, packed, flags);
             } else {
                 const size_t sl = sizeof(PackedEmit<2>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<2>) : sizeof(SmallEmit<unsigned short>);
                 UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
                 k_emit_small_packed<16><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
-                                                                                        out_u, out_v, edge_src_out, packed, guard);
+                                                                                        out_u, out_v, edge_src_out, packed, flags);
             }
         } else if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER)) {
             const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out, packed, guard);
+                                                                   nodes, edge_ptr, out_u, out_v, edge_src_out, packed, flags);
         } else {
             const size_t smem = sizeof(SmallEmit<u32>) * EMIT_WARPS;
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_emit_small<false><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, mode, tpi, ipg, use_perm, w,
-                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out, nullptr, guard);
+                                                                    nodes, edge_ptr, out_u, out_v, edge_src_out, nullptr, flags);
         }
         UGS_LAUNCH_CHECK("k_emit_small");
     }
@@ -1643,7 +1682,7 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
         if (blocks > cap) blocks = cap;
         k_emit_general<false><<<(unsigned)blocks, 256, 0, st>>>(ptr, node_base, m, k, mode, n_general, true, w, nodes,
                                                                const_cast<i64*>(edge_ptr), total, out_u, out_v,
-                                                               edge_src_out);
+                                                               edge_src_out, flags);
         UGS_LAUNCH_CHECK("k_emit_general");
     }
     return UGS_OK;

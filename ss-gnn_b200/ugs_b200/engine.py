@@ -448,7 +448,9 @@ class DeviceBatch:
 
 
 # ---- small batches: one library call, one host round trip (csrc/ugs_fused.cu) --------------------------------------
-FUSED_MAX_BYTES = 1 << 30     # worst-case output (24 bytes x 2E x m) up to which the fused path is taken
+FUSED_MAX_BYTES = 1 << 30
+# bound-sized edge arrays up to this size are handed out as the results themselves (views; no narrowing pass)
+FUSED_COMPACT_MAX_BYTES = int(os.environ.get("UGS_B200_FUSED_COMPACT_BYTES", 64 << 20))     # worst-case output (24 bytes x 2E x m) up to which the fused path is taken
 _fused_tls = threading.local()  # per thread and device: (pinned int64[64] tensor for the counters, its numpy view)
 
 
@@ -493,10 +495,19 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
         _lib.check(L.ugs_workspace_layout(E, G, NT, ctypes.byref(lay)))
         cap = int(L.ugs_fused_capacity(E, m))
         sbytes = int(L.ugs_sample_scratch_bytes(G, m))
-        # one temporary allocation: workspace | scan + packed-row scratch | bound-sized edge arrays
+        # one temporary allocation: workspace | scan + packed-row scratch | bound-sized edge arrays. Small bounds get the
+        # edge arrays as an allocation of their own that the emission kernels fill compactly (UGS_FUSED_COMPACT): the
+        # results are views of it and the narrowing pass (a launch behind the host round trip) is not needed.
         off_s = (lay.total_bytes + 255) & ~255
         off_e = off_s + ((sbytes + 255) & ~255)
-        tmp = torch.empty(off_e + 24 * cap, dtype=torch.uint8, device=dev)
+        compact = 24 * cap <= FUSED_COMPACT_MAX_BYTES
+        if compact:
+            tmp = torch.empty(off_e, dtype=torch.uint8, device=dev)
+            ebuf = torch.empty(3 * cap, dtype=torch.int64, device=dev)
+            e_base = ebuf.data_ptr()
+        else:
+            tmp = torch.empty(off_e + 24 * cap, dtype=torch.uint8, device=dev)
+            e_base = tmp.data_ptr() + off_e
         # the three outputs whose sizes do not depend on the samples share one allocation (so that a caller who wants
         # them on the host needs one copy): nodes | edge_ptr | sample_ptr
         fixed = torch.empty(B * k + (B + 1) + (G + 1), dtype=torch.int64, device=dev)
@@ -514,12 +525,13 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
         # the next one is queued without the general-path kernels, and repeated with them if the device count says the
         # guess was wrong (the outputs of the first attempt are void then).
         guess = 1 if (slots.get(("no_general", dev.index)) and k <= 16) else 0
+        cflag = 2 if compact else 0
         while True:
             rc = L.ugs_sample_batch_fused(
                 edge_index.data_ptr(), E, ptr.data_ptr(), G, int(node_base), NT, m, k, MODES[mode], seed & (2 ** 64 - 1),
                 int(graph_index_base), int(sample_index_base), 1 if per_graph_seed else 0, base, ctypes.byref(lay),
-                base + off_s, sbytes, nodes.data_ptr(), edge_ptr.data_ptr(), sample_ptr.data_ptr(), base + off_e,
-                base + off_e + 8 * cap, base + off_e + 16 * cap, cap, hi[0].data_ptr(), guess, stream)
+                base + off_s, sbytes, nodes.data_ptr(), edge_ptr.data_ptr(), sample_ptr.data_ptr(), e_base,
+                e_base + 8 * cap, e_base + 16 * cap, cap, hi[0].data_ptr(), guess | cflag, stream)
             if rc != 0:
                 _lib.check(rc)
             info = hi[1]
@@ -534,11 +546,14 @@ def sample_batch_fused(edge_index: torch.Tensor, ptr: torch.Tensor, m: int, k: i
         stats = dict(n_graphlets=B, n_edge_entries=total, n_incomplete=int(info[CTR["incomplete"]]),
                      n_relaxed_graphs=int(info[CTR["relaxed"]]), n_skipped_graphs=n_skipped,
                      n_general_graphs=int(info[CTR["n_general"]]), n_trials=(G - n_skipped) * m)
-        edges = torch.empty(3 * total, dtype=torch.int64, device=dev)  # edge_index rows | edge_src, one allocation
+        if compact:
+            edges = ebuf[:3 * total]  # edge_index rows | edge_src as the kernels wrote them
+        else:
+            edges = torch.empty(3 * total, dtype=torch.int64, device=dev)  # edge_index rows | edge_src, one allocation
         edge_index_out = edges[:2 * total].view(2, total)
         edge_src = edges[2 * total:]
-        if total > 0:
-            rc = L.ugs_fused_finish(base + off_e, base + off_e + 8 * cap, base + off_e + 16 * cap, total,
+        if total > 0 and not compact:
+            rc = L.ugs_fused_finish(e_base, e_base + 8 * cap, e_base + 16 * cap, total,
                                     edge_index_out.data_ptr(), edge_src.data_ptr(), stream)
             if rc != 0:
                 _lib.check(rc)

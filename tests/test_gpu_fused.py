@@ -115,3 +115,25 @@ def test_fused_guess_without_general_path_graphs_is_checked(cuda_lib):
                 assert torch.equal(a, b), name
             assert fs == ss
             assert _fused_tls.info[("no_general", dev)] == (ss["n_general_graphs"] == 0)
+
+
+def test_fused_compact_and_narrowed_results_agree(cuda_lib, monkeypatch):
+    """Bound-sized edge arrays up to FUSED_COMPACT_MAX_BYTES are filled compactly by the emission kernels (rows behind
+    one another at the device-side total; the results are views of that allocation); above it the bound-sized arrays are
+    narrowed by ugs_fused_finish. Same tensors either way, for odd and even totals, with general-path graphs in the batch."""
+    from ugs_b200 import engine, synth
+    rng = np.random.default_rng(5)
+    for ei, ptr in (random_batch(rng, 30, 1, 45, deg=2.5, big=[(5, 120)]), synth.make_batch("mutag", 25, seed=2),
+                    synth.make_batch("proteins", 20, seed=4)):
+        for m, k, mode in ((7, 4, "sample"), (16, 6, "global"), (3, 3, "graph")):
+            monkeypatch.setattr(engine, "FUSED_COMPACT_MAX_BYTES", 1 << 40)
+            co, cs = _fused(ei, ptr, m, k, mode, 11)
+            assert co[1].untyped_storage().nbytes() >= 24 * 2 * ei.shape[1] * m  # a view of the bound-sized array
+            monkeypatch.setattr(engine, "FUSED_COMPACT_MAX_BYTES", 0)
+            no, ns = _fused(ei, ptr, m, k, mode, 11)
+            assert no[1].untyped_storage().nbytes() == 24 * cs["n_edge_entries"]
+            so, ss = _staged(ei, ptr, m, k, mode, 11)
+            for name, a, b, c in zip(NAMES, co, no, so):
+                assert torch.equal(a, b) and torch.equal(a, c), (name, m, k, mode)
+                assert a.is_contiguous()
+            assert cs == ns == ss
