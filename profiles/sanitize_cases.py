@@ -37,5 +37,20 @@ DeviceBatch(d(ez), d(pz), 4, 0, int(pz[-1]), variant="uniform").sample(8, 4, "sa
 # APX-UGS with few trials
 edges = np.array([[0, 1], [1, 0], [1, 2], [2, 1], [2, 0], [0, 2], [2, 3], [3, 2], [3, 4], [4, 3]], np.int64).T.copy()
 apx_ugs_sampler.sample_batch(d(edges), torch.tensor([0, 10]).cuda(), 4, 3, "sample", 5, 0.5, _max_trials=2048)
+# PROTEINS-sized graphs: k_preproc_medium; enough general-path samples for the thread-per-sample kernel (k_sample_medium)
+ep, pp = synth.make_batch("proteins", 60, seed=2)
+DeviceBatch(d(ep), d(pp), 5, 0, int(pp[-1])).sample(1400, 5, "sample", seed=6)
+# general-path exact-uniform tables and sampler, random-walk sampler
+DeviceBatch(d(ep), d(pp), 4, 0, int(pp[-1]), variant="uniform").sample(4, 4, "sample", seed=7)
+DeviceBatch(d(ep), d(pp), 4, 0, int(pp[-1])).sample_rwr(6, 4, "sample", seed=8)
+# fused one-call path: guess / compact / narrowed, small and mixed batches, host delivery
+from ugs_b200 import engine
+from ugs_b200.engine import sample_batch_fused
+for e_, p_ in ((ez, pz), (ez, pz), (ep, pp), (ei, ptr)):
+    sample_batch_fused(d(e_), d(p_), 7, 4, "sample", 9, 0, int(p_[-1]))
+engine.FUSED_COMPACT_MAX_BYTES = 0
+sample_batch_fused(d(ep), d(pp), 7, 4, "global", 9, 0, int(pp[-1]))
+import ugs_sampler
+ugs_sampler.sample_batch(torch.from_numpy(ez), torch.from_numpy(pz), 8, 4, mode="sample", seed=3)
 torch.cuda.synchronize()
 print("sanitize_cases: done")
