@@ -167,6 +167,10 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // PROTEINS-sized general-path graphs: their tables fit a CTA's shared memory (k_preproc_medium, k_sample_medium)

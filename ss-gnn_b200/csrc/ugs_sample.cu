@@ -17,14 +17,56 @@
 #ifndef SAMP_MINB
 #define SAMP_MINB 4      // min resident CTAs per SM asked of the compiler (register budget)
 #endif
+#ifndef SAMP_PIPE
+#define SAMP_PIPE 1      // 1: large batches take the persistent kernel with cp.async fetch-ahead (k_sample_small_pipe)
+#endif
 #ifndef SAMP_VECSTORE
 #define SAMP_VECSTORE 1  // 1: every thread stores its own node row with 16-byte stores (even k <= 8)
 #endif
 
+
 // =====================================================================================================
 // Bitmask path: sample + count
 // =====================================================================================================
+// r-th set bit of a mask: three byte-prefix popcounts locate the byte, a 256 x 8 table gives the position inside it
+// (20 instructions against 33 for the five-level popcount search; A/B on the ZINC-shaped shard: 0.393 -> 0.368 ms).
+// The table is copied into shared memory once per CTA (2 KB): random byte reads there cost a few bank-conflict
+// replays, through L1 they cost one tag look-up per distinct line.
+struct SelLut { unsigned char p[256][8]; };
+static constexpr SelLut make_sel_lut() {
+    SelLut t{};
+    for (int b = 0; b < 256; ++b) {
+        int r = 0;
+        for (int j = 0; j < 8; ++j) t.p[b][j] = 0;
+        for (int j = 0; j < 8; ++j)
+            if ((b >> j) & 1) t.p[b][r++] = (unsigned char)j;
+    }
+    return t;
+}
+__device__ const SelLut g_sel_lut = make_sel_lut();
+
+// the threads of the CTA copy one 8-byte row each; the caller synchronises the CTA
+__device__ __forceinline__ void sel_lut_stage(unsigned char* lut) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x)
+        reinterpret_cast<u64*>(lut)[b] = reinterpret_cast<const u64*>(&g_sel_lut)[b];
+}
+
+__device__ __forceinline__ int select_bit_lut(const unsigned char* __restrict__ lut, u32 m, int r) {
+    const int c0 = __popc(m & 0xffu), c1 = __popc(m & 0xffffu), c2 = __popc(m & 0xffffffu);
+    const bool p0 = r >= c0, p1 = r >= c1, p2 = r >= c2;
+    const int bi = p2 ? 3 : p1 ? 2 : p0 ? 1 : 0;
+    const int base = p2 ? c2 : p1 ? c1 : p0 ? c0 : 0;
+    const u32 byte = __byte_perm(m, 0u, 0x4440u + (u32)bi);
+    return 8 * bi + (int)lut[byte * 8 + (u32)(r - base)];
+}
+__device__ __forceinline__ int select_bit_lut(const unsigned char* __restrict__ lut, u64 m, int r) {
+    const u32 lo = (u32)m;
+    const int c = __popc(lo);
+    const bool hi = r >= c;
+    return (hi ? 32 : 0) + select_bit_lut(lut, hi ? (u32)(m >> 32) : lo, hi ? r - c : r);
+}
 struct __align__(16) SmallSamp {
+    ugs_ginfo gi;  // 32 bytes, 16-byte aligned: read where needed instead of living in eight registers across the tile loop
     u64 adj[64];
     u64 suf[64];
     double cum[64];
@@ -34,9 +76,6 @@ struct __align__(16) SmallSamp {
     unsigned char idx[2 * UGS_SMALL_MAX_COLS];
 };
 
-// r-th set bit, for either mask width
-__device__ __forceinline__ int select_bit(u32 m, int r) { return select_bit32(m, r); }
-__device__ __forceinline__ int select_bit(u64 m, int r) { return select_bit64(m, r); }
 __device__ __forceinline__ int popc_m(u32 m) { return __popc(m); }
 __device__ __forceinline__ int popc_m(u64 m) { return __popcll(m); }
 
@@ -51,9 +90,12 @@ struct __align__(16) SlotSamp {
     unsigned char order[64];
 };
 
-template <typename MaskT, int KT, typename TabT, bool HAS_ROWS>
-__device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, int n, int k, u32 i, u32 c2, u32 c3,
-                                           u32 k0, u32 k1, u64& nlo, u64& nhi, i64& cnt, int& n_incomplete) {
+// rowptr / idx: the graph's CSR rows in shared memory (only read when gi.mult == 0), or nullptr.
+template <typename MaskT, int KT, typename TabT>
+__device__ __forceinline__ void sample_one(const TabT& s, const unsigned short* rowptr, const unsigned char* idx,
+                                           const unsigned char* __restrict__ lut, const ugs_ginfo& gi, int n, int k,
+                                           u32 i, u32 c2, u32 c3, u32 k0, u32 k1, u64& nlo, u64& nhi, i64& cnt,
+                                           int& n_incomplete) {
     const int kk = KT ? KT : k;
     Philox4 r = philox4x32_10(i, 0u, c2, c3, k0, k1);
     const double x = (gi.level == 0) ? root_x(r.x, r.y, gi.Z) : (double)__umulhi(r.x, (u32)gi.n_eligible);
@@ -70,6 +112,7 @@ __device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, i
     MaskT nbr = (MaskT)s.adj[v0];
     nlo = (nlo & ~0xFFull) | (u64)v0;
     int size = 1;
+    int pairs = 0;  // member pairs joined by an edge; uniform multiplicity, no self loop: entries = 2 * pairs * mult
 #pragma unroll
     for (int step = 1; step < (KT ? KT : 16); ++step) {
         if (step >= kk) break;
@@ -79,9 +122,11 @@ __device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, i
         const int wsel = (step + 1) & 3;
         if (wsel == 0) r = philox4x32_10(i, (u32)((step + 1) >> 2), c2, c3, k0, k1);
         const u32 wv = (wsel == 0) ? r.x : (wsel == 1) ? r.y : (wsel == 2) ? r.z : r.w;
-        const int xnew = select_bit(cut, (int)__umulhi(wv, (u32)c));
+        const int xnew = select_bit_lut(lut, cut, (int)__umulhi(wv, (u32)c));
+        const MaskT ax = (MaskT)s.adj[xnew];
+        pairs += popc_m(ax & S);
         S |= (MaskT)1 << xnew;
-        nbr |= (MaskT)s.adj[xnew];
+        nbr |= ax;
         if (step < 8) nlo = (nlo & ~(0xFFull << (8 * step))) | ((u64)xnew << (8 * step));
         else nhi = (nhi & ~(0xFFull << (8 * (step - 8)))) | ((u64)xnew << (8 * (step - 8)));
         size++;
@@ -89,17 +134,11 @@ __device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, i
     if (size == kk) {
         int c = 0;
         if (gi.mult > 0) {
-#pragma unroll
-            for (int j = 0; j < (KT ? KT : 16); ++j) {
-                if (j >= kk) break;
-                const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                c += popc_m((MaskT)s.adj[v] & S);
-            }
-            c *= gi.mult;
-        } else if constexpr (HAS_ROWS) {
+            c = 2 * pairs * gi.mult;
+        } else if (rowptr) {
             for (int j = 0; j < kk; ++j) {
                 const int v = (int)(((j < 8) ? (nlo >> (8 * j)) : (nhi >> (8 * (j - 8)))) & 0xFF);
-                for (int p = s.rowptr[v]; p < s.rowptr[v + 1]; ++p) c += (int)((S >> s.idx[p]) & (MaskT)1);
+                for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) c += (int)((S >> idx[p]) & (MaskT)1);
             }
         }
         cnt = c;
@@ -108,19 +147,115 @@ __device__ __forceinline__ void sample_one(const TabT& s, const ugs_ginfo& gi, i
     }
 }
 
-// All samples of tiles [t0, t1) of graph g, one thread per sample, by one warp whose shared-memory slice is `s`.
+// Rows of a skipped graph (n <= 0 or n < k): m rows of -1, no edges (ugs_sampler_batch_extension.cpp:132-143).
+__device__ __forceinline__ void sample_rows_skipped(i64 g, int t0, int t1, i64 m, int k, i64* __restrict__ nodes_out,
+                                                    i64* __restrict__ edge_ptr, u64* __restrict__ packed) {
+    const int lane = threadIdx.x & 31;
+    for (int t = t0; t < t1; ++t) {
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+        for (int e = lane; e < nv * k; e += 32) nodes_out[s0 * k + e] = -1;
+        if (lane < nv) edge_ptr[1 + s0 + lane] = 0;
+        if (packed && lane < nv) packed[s0 + lane] = ~0ull;
+    }
+}
+
+// All samples of tiles [t0, t1) of graph g (its tables already in shared memory: `s`), one thread per sample.
+template <int KT, typename TabT>
+__device__ __forceinline__ void sample_tiles_staged(const TabT& s, const unsigned short* rowptr, const unsigned char* idx,
+                                                    const unsigned char* __restrict__ lut,
+                                                    unsigned char (*tile)[16], const ugs_ginfo& gi, i64 g,
+                                                    i64 lo, int n, int t0, int t1, bool first_chunk, i64 m, int k,
+                                                    u64 seed, u64 gbase, u32 ibase, int seed_mode, const WS& w,
+                                                    i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr,
+                                                    u64* __restrict__ packed) {
+    const int lane = threadIdx.x & 31;
+    const int r32 = 32 % k, q32 = 32 / k;
+    const u64 gidx = gbase + (u64)g;
+    // seed_mode 1: key = seed + graph index, graph counter 0 -- what a loop of single-graph calls with seed + i draws
+    const u64 kseed = seed_mode ? seed + gidx : seed;
+    const u64 cg = seed_mode ? 0ull : gidx;
+    const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
+    int n_incomplete = 0;
+    int cnt_sum = 0;  // this lane's emitted-entry count over the item's tiles (early total, see UGS_CTR_EARLY_TOTAL)
+
+    for (int t = t0; t < t1; ++t) {
+        const i64 i = (i64)t * 32 + lane;  // sample index inside the graph
+        const bool active = i < m;
+        u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
+        i64 cnt = 0;
+        if (active) {
+            if (n <= 32) sample_one<u32, KT, TabT>(s, rowptr, idx, lut, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+            else sample_one<u64, KT, TabT>(s, rowptr, idx, lut, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+        }
+        const i64 s0 = g * m + (i64)t * 32;
+        const int nv = (int)min((i64)32, m - (i64)t * 32);
+        if (packed && active) packed[s0 + lane] = nlo;  // the emission pass reads 8 bytes per sample instead of 8k
+        cnt_sum += (int)cnt;
+#if SAMP_VECSTORE
+        if (KT > 0 && KT <= 8 && (KT & 1) == 0) {
+            // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
+            if (active) {
+                longlong2* out = reinterpret_cast<longlong2*>(nodes_out + (s0 + lane) * KT);
+                if (((nlo >> (8 * (KT - 1))) & 0xFFull) != 0xFFull) {  // complete row: the last entry is set, so all are
+#pragma unroll
+                    for (int q = 0; q < KT / 2; ++q)
+                        out[q] = make_longlong2(lo + (i64)((u32)(nlo >> (16 * q)) & 0xFFu),
+                                                lo + (i64)((u32)(nlo >> (16 * q + 8)) & 0xFFu));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < KT / 2; ++q) {
+                        const u32 b0 = (u32)(nlo >> (16 * q)) & 0xFFu, b1 = (u32)(nlo >> (16 * q + 8)) & 0xFFu;
+                        out[q] = make_longlong2((b0 == 0xFFu) ? (i64)-1 : lo + (i64)b0, (b1 == 0xFFu) ? (i64)-1 : lo + (i64)b1);
+                    }
+                }
+            }
+        } else
+#endif
+        {
+            // ---- coalesced output through the shared tile ------------------------------------------------
+            *reinterpret_cast<ulonglong2*>(&tile[lane][0]) = make_ulonglong2(nlo, nhi);
+            __syncwarp();
+            int sidx = lane / k, j = lane - sidx * k;
+            i64* out = nodes_out + s0 * k;
+            for (int e = lane; e < nv * k; e += 32) {
+                const unsigned char bv = tile[sidx][j];
+                out[e] = (bv == 0xFF) ? (i64)-1 : lo + (i64)bv;  // batch ext :194 adds lo
+                j += r32; sidx += q32;
+                if (j >= k) { j -= k; sidx++; }
+            }
+        }
+        if (active) edge_ptr[1 + s0 + lane] = cnt;
+        __syncwarp();
+    }
+    // statistics (the only cross-rank exchange later all-gathers these)
+    n_incomplete = __reduce_add_sync(FULL_MASK, n_incomplete);
+    cnt_sum = __reduce_add_sync(FULL_MASK, cnt_sum);
+    if (lane == 0 && cnt_sum)
+        atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], (unsigned long long)cnt_sum);
+    if (lane == 0) {
+        if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
+        if (first_chunk && gi.level > 0) atomicAdd(&w.counters[UGS_CTR_RELAXED], 1ull);
+    }
+}
+
+// Tiles [t0, t1) of graph g by one warp that stages the graph's tables into its shared-memory slice `s` first.
 template <int KT>
 __device__ __forceinline__ void sample_graph_tiles(SmallSamp& s, i64 g, int chunk, int tiles_per_item,
                                                    const i64* __restrict__ ptr, i64 node_base, i64 m, int k, u64 seed,
                                                    u64 gbase, u32 ibase, int seed_mode, const WS& w,
                                                    i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr,
-                                                   i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
+                                                   i64* __restrict__ sample_ptr, u64* __restrict__ packed,
+                                                   const unsigned char* __restrict__ lut) {
     const int lane = threadIdx.x & 31;
     if (chunk == 0 && lane == 0) {
         sample_ptr[g + 1] = (g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
         if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
     }
-    const ugs_ginfo gi = w.ginfo[g];
+    __syncwarp();  // a previous graph of this warp (k_sample_small_packed) is done with the slice
+    if (lane < 2) reinterpret_cast<ulonglong2*>(&s.gi)[lane] = reinterpret_cast<const ulonglong2*>(&w.ginfo[g])[lane];
+    __syncwarp();
+    const ugs_ginfo& gi = s.gi;
     if (gi.cls == 2) return;
     if (gi.cls == 1 && k > 16) {  // the workspace was preprocessed for a smaller k: tile[][16] cannot hold the row
         if (lane == 0) atomicOr(&w.counters[UGS_CTR_UNSORTED], 16ull);
@@ -128,20 +263,11 @@ __device__ __forceinline__ void sample_graph_tiles(SmallSamp& s, i64 g, int chun
     }
     const int ntiles = (int)((m + 31) >> 5);
     const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
-    const i64 lo = ptr[g];
-    const int r32 = 32 % k, q32 = 32 / k;
-
-    if (gi.cls == 0) {  // n <= 0 or n < k: m rows of -1, no edges (:132-143)
-        for (int t = t0; t < t1; ++t) {
-            const i64 s0 = g * m + (i64)t * 32;
-            const int nv = (int)min((i64)32, m - (i64)t * 32);
-            for (int e = lane; e < nv * k; e += 32) nodes_out[s0 * k + e] = -1;
-            if (lane < nv) edge_ptr[1 + s0 + lane] = 0;
-            if (packed && lane < nv) packed[s0 + lane] = ~0ull;
-        }
+    if (gi.cls == 0) {
+        sample_rows_skipped(g, t0, t1, m, k, nodes_out, edge_ptr, packed);
         return;
     }
-
+    const i64 lo = ptr[g];
     const int n = (int)(ptr[g + 1] - lo);
     const i64 nb = lo - node_base;
 #pragma unroll
@@ -161,69 +287,8 @@ __device__ __forceinline__ void sample_graph_tiles(SmallSamp& s, i64 g, int chun
         for (int p = lane; p < gi.nnz; p += 32) s.idx[p] = (unsigned char)ci[p];
     }
     __syncwarp();
-
-    const u64 gidx = gbase + (u64)g;
-    // seed_mode 1: key = seed + graph index, graph counter 0 -- what a loop of single-graph calls with seed + i draws
-    const u64 kseed = seed_mode ? seed + gidx : seed;
-    const u64 cg = seed_mode ? 0ull : gidx;
-    const u32 c2 = (u32)cg, c3 = (u32)(cg >> 32), k0 = (u32)kseed, k1 = (u32)(kseed >> 32);
-    int n_incomplete = 0;
-    i64 cnt_sum = 0;  // this lane's emitted-entry count over the item's tiles (early total, see UGS_CTR_EARLY_TOTAL)
-
-    for (int t = t0; t < t1; ++t) {
-        const i64 i = (i64)t * 32 + lane;  // sample index inside the graph
-        const bool active = i < m;
-        u64 nlo = ~0ull, nhi = ~0ull;      // packed node bytes, 0xFF = -1
-        i64 cnt = 0;
-        if (active) {
-            if (n <= 32) sample_one<u32, KT, SmallSamp, true>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
-            else sample_one<u64, KT, SmallSamp, true>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
-        }
-        const i64 s0 = g * m + (i64)t * 32;
-        const int nv = (int)min((i64)32, m - (i64)t * 32);
-        if (packed && active) packed[s0 + lane] = nlo;  // the emission pass reads 8 bytes per sample instead of 8k
-        cnt_sum += cnt;
-#if SAMP_VECSTORE
-        if (KT > 0 && KT <= 8 && (KT & 1) == 0) {
-            // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
-            if (active) {
-                longlong2* out = reinterpret_cast<longlong2*>(nodes_out + (s0 + lane) * KT);
-#pragma unroll
-                for (int q = 0; q < KT / 2; ++q) {
-                    const u32 b0 = (u32)(nlo >> (16 * q)) & 0xFFu, b1 = (u32)(nlo >> (16 * q + 8)) & 0xFFu;
-                    out[q] = make_longlong2((b0 == 0xFFu) ? (i64)-1 : lo + (i64)b0, (b1 == 0xFFu) ? (i64)-1 : lo + (i64)b1);
-                }
-            }
-        } else
-#endif
-        {
-        // ---- coalesced output through the shared tile ------------------------------------------------
-        *reinterpret_cast<ulonglong2*>(&s.tile[lane][0]) = make_ulonglong2(nlo, nhi);
-        __syncwarp();
-        {
-            int sidx = lane / k, j = lane - sidx * k;
-            i64* out = nodes_out + s0 * k;
-            for (int e = lane; e < nv * k; e += 32) {
-                const unsigned char bv = s.tile[sidx][j];
-                out[e] = (bv == 0xFF) ? (i64)-1 : lo + (i64)bv;  // batch ext :194 adds lo
-                j += r32; sidx += q32;
-                if (j >= k) { j -= k; sidx++; }
-            }
-        }
-        }
-        if (active) edge_ptr[1 + s0 + lane] = cnt;
-        __syncwarp();
-    }
-    // statistics (the only cross-rank exchange later all-gathers these)
-    n_incomplete = __reduce_add_sync(FULL_MASK, n_incomplete);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) cnt_sum += __shfl_xor_sync(FULL_MASK, cnt_sum, off);
-    if (lane == 0 && cnt_sum)
-        atomicAdd(&w.counters[UGS_CTR_EARLY_TOTAL + (blockIdx.x & (UGS_CTR_EARLY_SLOTS - 1))], (unsigned long long)cnt_sum);
-    if (lane == 0) {
-        if (n_incomplete) atomicAdd(&w.counters[UGS_CTR_INCOMPLETE], (unsigned long long)n_incomplete);
-        if (chunk == 0 && gi.level > 0) atomicAdd(&w.counters[UGS_CTR_RELAXED], 1ull);
-    }
+    sample_tiles_staged<KT, SmallSamp>(s, s.rowptr, s.idx, lut, s.tile, gi, g, lo, n, t0, t1, chunk == 0, m, k, seed, gbase, ibase, seed_mode, w,
+                                       nodes_out, edge_ptr, packed);
 }
 
 template <int KT>
@@ -232,14 +297,124 @@ k_sample_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, 
                int seed_mode, int tiles_per_item, i64 items_per_graph, WS w, i64* __restrict__ nodes_out,
                i64* __restrict__ edge_ptr, i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
     __shared__ SmallSamp sm_all[SAMP_WARPS];
+    __shared__ __align__(16) unsigned char lut[2048];
     if (KT) k = KT;
+    sel_lut_stage(lut);
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     const i64 item = (i64)blockIdx.x * SAMP_WARPS + warp;
     const i64 g = (items_per_graph == 1) ? item : item / items_per_graph;
     if (g >= G) return;
     const int chunk = (int)(item - g * items_per_graph);
     sample_graph_tiles<KT>(sm_all[warp], g, chunk, tiles_per_item, ptr, node_base, m, k, seed, gbase, ibase, seed_mode, w,
-                           nodes_out, edge_ptr, sample_ptr, packed);
+                           nodes_out, edge_ptr, sample_ptr, packed, lut);
+}
+
+// Large batches (at least two graphs per resident warp, every tile of a graph in one item): PERSISTENT warps that walk
+// the graphs round-robin and fetch ahead with cp.async. Staging is three dependent global round trips (ginfo / ptr ->
+// table addresses -> tables) and a quarter of the warp-time of k_sample_small (long-scoreboard stalls; one tile per
+// staging instead of two costs +0.07 ms on the ZINC-shaped shard). Here, while graph j is sampled, the tables of graph
+// j+1 (into the other buffer) and the ginfo / ptr pair of graph j+2 (a three-slot ring) are in flight; nothing is held
+// in registers for them.
+struct __align__(16) PipeTab {
+    u64 adj[64];
+    u64 suf[64];
+    double cum[64];
+    i32 order[64];
+};
+struct __align__(16) PipeWarp {
+    PipeTab tab[2];
+    ugs_ginfo gi[3];
+    i64 pp[3][2];
+    unsigned char tile[32][16];
+    unsigned short rowptr[66];  // rowptr / idx: graphs with irregular multiplicities only, staged when the graph's turn comes
+    unsigned char idx[2 * UGS_SMALL_MAX_COLS];
+};
+
+template <int KT>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, SAMP_MINB)
+k_sample_small_pipe(const i64* __restrict__ ptr, int G, i64 node_base, i64 m, int k, u64 seed, u64 gbase, u32 ibase,
+                    int seed_mode, WS w, i64* __restrict__ nodes_out, i64* __restrict__ edge_ptr,
+                    i64* __restrict__ sample_ptr, u64* __restrict__ packed) {
+    __shared__ PipeWarp sm_all[SAMP_WARPS];
+    __shared__ __align__(16) unsigned char lut[2048];
+    if (KT) k = KT;
+    sel_lut_stage(lut);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PipeWarp& pw = sm_all[warp];
+#define W ((int)gridDim.x * SAMP_WARPS)
+    int g = (int)blockIdx.x * SAMP_WARPS + warp;
+    if (g >= G) return;
+    const int ntiles = (int)((m + 31) >> 5);
+
+    // ginfo (32 bytes) and the ptr pair of graph gg -> ring slot
+    auto fetch_meta = [&](int gg, int slot) {
+        if (gg < G) {
+            if (lane < 2) cp_async_8(&pw.pp[slot][lane], ptr + gg + lane);
+            else if (lane < 4) cp_async_16(reinterpret_cast<char*>(&pw.gi[slot]) + 16 * (lane - 2),
+                                           reinterpret_cast<const char*>(&w.ginfo[gg]) + 16 * (lane - 2));
+        }
+    };
+    // tables of the graph whose meta data sit in `slot` -> buffer `buf` (bitmask-path graphs only: n <= 64)
+    auto fetch_tabs = [&](int slot, int buf) {
+        if (pw.gi[slot].cls != 1) return;
+        const i64 lo = pw.pp[slot][0];
+        const int n = min((int)(pw.pp[slot][1] - lo), UGS_SMALL_MAX_N);
+        const i64 nb = lo - node_base;
+        PipeTab& tb = pw.tab[buf];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int v = lane + 32 * h;
+            if (v < n) {
+                cp_async_8(&tb.adj[v], w.adj + nb + v);
+                cp_async_8(&tb.suf[v], w.suf + nb + v);
+                cp_async_8(&tb.cum[v], w.cum + nb + v);
+                cp_async_4(&tb.order[v], w.order + nb + v);
+            }
+        }
+    };
+
+    fetch_meta(g, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    fetch_tabs(0, 0);
+    fetch_meta(g + W, 1);
+    int slot = 0, buf = 0;
+    for (; g < G; g += W) {
+        cp_async_wait_all();  // tables of this graph, meta data of the next
+        __syncwarp();         // ... visible to every lane; and every lane is done with the previous graph's buffers
+        const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
+        if (g + W < G) fetch_tabs(slot1, buf ^ 1);
+        fetch_meta(g + 2 * W, slot2);
+
+        if (lane == 0) {
+            sample_ptr[g + 1] = ((i64)g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
+            if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
+        }
+        const ugs_ginfo& gi = pw.gi[slot];  // read from shared memory where needed, not held in registers
+        if (gi.cls == 1 && k > 16) {
+            if (lane == 0) atomicOr(&w.counters[UGS_CTR_UNSORTED], 16ull);
+        } else if (gi.cls == 0) {
+            sample_rows_skipped(g, 0, ntiles, m, k, nodes_out, edge_ptr, packed);
+        } else if (gi.cls == 1) {
+            const i64 lo = pw.pp[slot][0];
+            const int n = (int)(pw.pp[slot][1] - lo);
+            PipeTab& tb = pw.tab[buf];
+            if (gi.mult == 0) {
+                const u32* rp = w.rowptr + (lo - node_base) + g;
+                const i32* ci = w.csr_idx + 2 * w.cstart[g];
+                for (int v = lane; v <= n; v += 32) pw.rowptr[v] = (unsigned short)rp[v];
+                for (int p = lane; p < gi.nnz; p += 32) pw.idx[p] = (unsigned char)ci[p];
+                __syncwarp();
+            }
+            sample_tiles_staged<KT, PipeTab>(tb, pw.rowptr, pw.idx, lut, pw.tile, gi, g, lo, n, 0, ntiles, true, m, k, seed, gbase, ibase, seed_mode,
+                                             w, nodes_out, edge_ptr, packed);
+        }
+        slot = slot1;
+        buf ^= 1;
+    }
+#undef W
 }
 
 // m <= 16 samples per graph (QM9-style completeness runs: m = 10) leave most lanes of a (graph, 32-sample tile) warp
@@ -255,7 +430,10 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
     constexpr size_t SLICE = (sizeof(SlotSamp) * GPW > sizeof(SmallSamp)) ? sizeof(SlotSamp) * GPW : sizeof(SmallSamp);
     extern __shared__ __align__(16) unsigned char packed_smem_raw[];  // SAMP_WARPS x SLICE (51 KB for S = 8)
     unsigned char (*raw)[SLICE] = reinterpret_cast<unsigned char (*)[SLICE]>(packed_smem_raw);
+    unsigned char* lut = packed_smem_raw + SAMP_WARPS * SLICE;  // 2 KB behind the slices
     if (KT) k = KT;
+    sel_lut_stage(lut);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = lane / S, i = lane - slot * S;
     const i64 g_first = ((i64)blockIdx.x * SAMP_WARPS + warp) * GPW;
@@ -268,7 +446,7 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
     if (__any_sync(FULL_MASK, valid && gi.cls == 1 && (gi.mult <= 0 || k > 16))) {
         for (int sl = 0; sl < GPW && g_first + sl < G; ++sl) {
             sample_graph_tiles<KT>(*reinterpret_cast<SmallSamp*>(raw[warp]), g_first + sl, 0, 1, ptr, node_base, m, k, seed,
-                                   gbase, ibase, seed_mode, w, nodes_out, edge_ptr, sample_ptr, packed);
+                                   gbase, ibase, seed_mode, w, nodes_out, edge_ptr, sample_ptr, packed, lut);
             __syncwarp();
         }
         return;
@@ -299,8 +477,8 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
     u64 nlo = ~0ull, nhi = ~0ull;
     i64 cnt = 0;
     if (live && active) {
-        if (narrow) sample_one<u32, KT, SlotSamp, false>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
-        else sample_one<u64, KT, SlotSamp, false>(s, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+        if (narrow) sample_one<u32, KT, SlotSamp>(s, nullptr, nullptr, lut, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
+        else sample_one<u64, KT, SlotSamp>(s, nullptr, nullptr, lut, gi, n, k, (u32)i + ibase, c2, c3, k0, k1, nlo, nhi, cnt, n_incomplete);
     }
     if (active && (gi.cls == 0 || gi.cls == 1)) {  // cls 0: n < k, rows of -1 (:132-143); cls 2: the general kernel's
         const i64 row = g * m + i;
@@ -1493,7 +1671,7 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
         const int64_t warps = (G + 32 / S - 1) / (32 / S);
         const unsigned grid = (unsigned)((warps + SAMP_WARPS - 1) / SAMP_WARPS);
         const size_t slice = (sizeof(SlotSamp) * (32 / S) > sizeof(SmallSamp)) ? sizeof(SlotSamp) * (32 / S) : sizeof(SmallSamp);
-        const size_t psmem = slice * SAMP_WARPS;
+        const size_t psmem = ((slice + 15) & ~(size_t)15) * SAMP_WARPS + 2048;  // + the select table
 #define UGS_LAUNCH_PACKED(KT_)                                                                                          \
     do {                                                                                                                \
         if (S == 8) {                                                                                                   \
@@ -1520,6 +1698,22 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
         }
 #undef UGS_LAUNCH_PACKED
         UGS_LAUNCH_CHECK("k_sample_small_packed");
+    } else if (SAMP_PIPE && ipg == 1 && G < (1ll << 31) && G >= 2ll * sm_count() * SAMP_MINB * SAMP_WARPS) {
+        // persistent warps with cp.async fetch-ahead: at least two graphs per resident warp
+        const unsigned grid = (unsigned)(sm_count() * SAMP_MINB);
+#define UGS_LAUNCH_PIPE(KT_)                                                                                          \
+    k_sample_small_pipe<KT_><<<grid, SAMP_WARPS * 32, 0, st>>>(ptr, (int)G, node_base, m, k, seed, graph_index_base,   \
+                                                                 ibase, seed_mode, w, nodes, edge_ptr, sample_ptr, packed)
+        switch (k) {
+            case 3: UGS_LAUNCH_PIPE(3); break;
+            case 4: UGS_LAUNCH_PIPE(4); break;
+            case 5: UGS_LAUNCH_PIPE(5); break;
+            case 6: UGS_LAUNCH_PIPE(6); break;
+            case 8: UGS_LAUNCH_PIPE(8); break;
+            default: UGS_LAUNCH_PIPE(0); break;
+        }
+#undef UGS_LAUNCH_PIPE
+        UGS_LAUNCH_CHECK("k_sample_small_pipe");
     } else {
         const int64_t items = G * ipg;
         const unsigned grid = (unsigned)((items + SAMP_WARPS - 1) / SAMP_WARPS);
