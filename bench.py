@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (other BASELINE configs)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained loop (0 = skip)")
+    ap.add_argument("--prewarm-seconds", type=float, default=1.0, help="untimed load before the warm-up steps (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -437,6 +438,14 @@ def main():
     clk = ClockSampler(local_rank)
     if rank == 0:  # one sampler per job: nvidia-smi takes a driver lock, N of them perturb the other ranks' launches
         clk.__enter__()  # sampled from the warm-up to the end of the e2e leg (the timed regions are milliseconds long)
+    # Pre-warm: a fresh process on an idle GPU needs a few hundred milliseconds of load before SM and memory clocks and
+    # the allocator's block sizes are those of a running job (measured: the first 20 steps after 10 warm-up steps ran at
+    # 2.02 ms, the same steps after 2 s of load at 1.79 ms). Untimed, before the W warm-up steps, stated in `config`.
+    t_pw = time.perf_counter()
+    n_pw = 0
+    while time.perf_counter() - t_pw < args.prewarm_seconds:
+        step(50000 + n_pw, False)
+        n_pw += 1
     for w in range(args.warmup):
         step(100 + w, False)
     # Allocator warm-up: the size of edge_index / edge_src is data dependent (it changes by ~0.01 % with the seed), and
@@ -658,6 +667,7 @@ def main():
                 "workload": workload_name(args.workload, G),
                 "k": k, "m": m, "graphs_per_rank": G, "nodes_per_rank": NT, "edge_columns_per_rank": E,
                 "mean_edge_entries_per_graphlet": ebar, "l2": "512 MiB flush between timed iterations",
+                "prewarm": f"{args.prewarm_seconds:g} s of untimed steps before the {args.warmup} warm-up steps",
                 "sharding": (f"dp{world} by sample of one replicated graph (m={m_job} split), no data-path collective"
                              if sample_sharded else f"dp{world} by graph, no data-path collective"),
             },

@@ -134,6 +134,226 @@ struct __align__(16) SmallPre {
     unsigned char index_of[64];
 };
 
+__device__ __forceinline__ int popc_t(u32 m) { return __popc(m); }
+__device__ __forceinline__ int popc_t(u64 m) { return __popcll(m); }
+__device__ __forceinline__ int ffs_t(u32 m) { return __ffs((int)m); }
+__device__ __forceinline__ int ffs_t(u64 m) { return __ffsll((long long)m); }
+
+// MaskT = u32: n <= 32, vertex / position `lane` only; MaskT = u64: vertices / positions lane and lane + 32.
+template <int KT, typename MaskT>
+__device__ __forceinline__ void preproc_small_tail(SmallPre& s, int n, int k, int nnz, i64 nb, i64 g, i64 csr_base,
+                                                   const WS& w) {
+    constexpr bool NARROW = sizeof(MaskT) == 4;
+    constexpr int H = NARROW ? 1 : 2;
+    const int lane = threadIdx.x & 31;
+    const u32 lt_mask = (1u << lane) - 1u;
+    // ---- A.3 order = stable sort by (degree, id): a counting sort over the DISTINCT degree values (a molecule has four
+    //      or five of them): per value two ballots give every vertex of that degree its rank, ids ascending because
+    //      lane order is id order (vertices lane and lane + 32).
+    {
+        const u32 none = 0xFFFFFFFFu;
+        const u32 d0 = (lane < n) ? s.deg[lane] : none;
+        const u32 d1 = (!NARROW && lane + 32 < n) ? s.deg[lane + 32] : none;
+        int base = 0;
+        u32 cur = 0;
+        bool first = true;
+        while (base < n) {
+            const u32 c0 = (d0 != none && (first || d0 > cur)) ? d0 : none;
+            const u32 c1 = (!NARROW && d1 != none && (first || d1 > cur)) ? d1 : none;
+            const u32 mn = __reduce_min_sync(FULL_MASK, NARROW ? c0 : min(c0, c1));
+            const u32 b0 = __ballot_sync(FULL_MASK, d0 == mn);
+            const u32 b1 = NARROW ? 0u : __ballot_sync(FULL_MASK, d1 == mn);
+            if (d0 == mn) {
+                const int rank = base + __popc(b0 & lt_mask);
+                s.order[rank] = (unsigned char)lane;
+                s.index_of[lane] = (unsigned char)rank;
+            }
+            if (!NARROW && d1 == mn) {
+                const int rank = base + __popc(b0) + __popc(b1 & lt_mask);
+                s.order[rank] = (unsigned char)(lane + 32);
+                s.index_of[lane + 32] = (unsigned char)rank;
+            }
+            base += __popc(b0) + __popc(b1);
+            cur = mn;
+            first = false;
+        }
+    }
+    __syncwarp();
+    // ---- suffix masks: suf[vi] = { order[vj] : vj >= vi } ----------------------------------------
+    if constexpr (NARROW) {
+        u32 x = (lane < n) ? (1u << s.order[lane]) : 0u;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 y = __shfl_down_sync(FULL_MASK, x, off);
+            if (lane + off < 32) x |= y;
+        }
+        s.suf[lane] = (u64)x;
+    } else {
+        u64 xh = (lane + 32 < n) ? (1ull << s.order[lane + 32]) : 0ull;
+        u64 xl = (lane < n) ? (1ull << s.order[lane]) : 0ull;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            u64 yh = __shfl_down_sync(FULL_MASK, xh, off);
+            u64 yl = __shfl_down_sync(FULL_MASK, xl, off);
+            if (lane + off < 32) { xh |= yh; xl |= yl; }
+        }
+        xl |= __shfl_sync(FULL_MASK, xh, 0);
+        s.suf[lane] = xl;
+        s.suf[lane + 32] = xh;
+    }
+    __syncwarp();
+    // ---- A.4 suffix degree, reachability (bounded BFS as a bitmask closure), weight; the same walk over row(v) also
+    //      classifies the row's multiplicities (every neighbour once / twice / both patterns, no self loop) ----------
+    int n0 = 0, n1 = 0, lastv = -1;
+    bool self_or_bad = false;
+    int mu_min = 99, mu_max = 0;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const int vi = lane + 32 * h;
+        double b = 0.0;
+        int sd = 0;
+        if (vi < n) {
+            const int v = s.order[vi];
+            const int p0 = s.rowptr[v], p1 = s.rowptr[v + 1];
+            MaskT ones = 0, twos = 0, fours = 0;
+            for (int p = p0; p < p1; ++p) {
+                const int x = s.idx[p];
+                sd += (s.index_of[x] >= vi) ? 1 : 0;
+                if (x == v) self_or_bad = true;
+                const MaskT bit = (MaskT)1 << x;
+                const MaskT cy0 = ones & bit; ones ^= bit;
+                const MaskT cy1 = twos & cy0; twos ^= cy0;
+                fours |= cy1;
+            }
+            const MaskT A = (MaskT)s.adj[v];
+            if (A) {
+                int mu = 0;
+                if (fours) mu = 0;
+                else if (ones == A && twos == 0) mu = 1;
+                else if (twos == A && ones == 0) mu = 2;
+                else if (ones == A && twos == A) mu = 3;
+                if (mu == 0) self_or_bad = true;
+                else { mu_min = min(mu_min, mu); mu_max = max(mu_max, mu); }
+            }
+            const MaskT sufm = (MaskT)s.suf[vi];
+            MaskT vis = (MaskT)1 << v, expd = 0;
+            bool reach = false;
+#pragma unroll
+            for (int it = 0; it < (KT ? KT : 16); ++it) {
+                if (it >= k) break;
+                if (popc_t(vis) >= k) { reach = true; break; }
+                const MaskT fr = vis & ~expd;
+                if (!fr) break;
+                const int u = ffs_t(fr) - 1;
+                expd |= (MaskT)1 << u;
+                vis |= (MaskT)s.adj[u] & sufm;
+            }
+            if (reach) {
+                const double d = (double)(sd > 1 ? sd : 1);
+                b = 1.0;
+#pragma unroll
+                for (int t = 0; t < (KT ? KT - 1 : 15); ++t) {  // preproc.cpp:228-233: k - 1 sequential multiplies
+                    if (t >= k - 1) break;
+                    b *= d;
+                }
+            }
+            if (b > 0.0) { n0++; lastv = vi; }
+            if (sd > 0) n1++;
+        }
+        s.b[vi] = b;
+        s.sd[vi] = (unsigned short)sd;
+    }
+    __syncwarp();
+    n0 = __reduce_add_sync(FULL_MASK, n0);
+    n1 = __reduce_add_sync(FULL_MASK, n1);
+    lastv = __reduce_max_sync(FULL_MASK, lastv);
+    mu_min = __reduce_min_sync(FULL_MASK, mu_min);
+    mu_max = __reduce_max_sync(FULL_MASK, mu_max);
+    self_or_bad = __any_sync(FULL_MASK, self_or_bad);
+    int mult = 0;
+    if (!self_or_bad) mult = (mu_max == 0) ? 1 : (mu_min == mu_max ? mu_min : 0);
+    const int level = (n0 > 0) ? 0 : ((n1 > 0) ? 1 : 2);
+
+    // ---- Z and the root CDF. Every weight is an integer-valued double; if the total is <= 2^53 every
+    //      partial sum is exact, so the parallel prefix equals the reference's left-to-right sum (:234).
+    //      NARROW: lane holds position lane (cum0); else positions 2*lane and 2*lane+1 (cum0, cum1).
+    double cum0, cum1 = 0.0, Z;
+    {
+        const double p0 = NARROW ? s.b[lane] : s.b[2 * lane], p1 = NARROW ? 0.0 : s.b[2 * lane + 1];
+        double incl = p0 + p1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            double y = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += y;
+        }
+        const double total = __shfl_sync(FULL_MASK, incl, 31);
+        if (total <= 9007199254740992.0) {
+            const double excl = incl - (p0 + p1);
+            cum0 = excl + p0;
+            cum1 = cum0 + p1;
+            Z = total;
+        } else {
+            double run = 0.0;
+            cum0 = cum1 = 0.0;
+            for (int vi = 0; vi < 32 * H; ++vi) {  // sequential, identical on every lane
+                run += s.b[vi];
+                if (vi == (NARROW ? lane : 2 * lane)) cum0 = run;
+                if (!NARROW && vi == 2 * lane + 1) cum1 = run;
+            }
+            Z = run;
+        }
+    }
+    if (level == 1) {
+        const u32 blo = __ballot_sync(FULL_MASK, s.sd[lane] > 0);
+        if constexpr (NARROW) {
+            cum0 = (double)__popc(blo & (0xffffffffu >> (31 - lane)));
+        } else {
+            const u32 bhi = __ballot_sync(FULL_MASK, s.sd[lane + 32] > 0);
+            // positions 2*lane and 2*lane+1
+            const int a = 2 * lane, bb = 2 * lane + 1;
+            auto pref = [&](int vi) -> double {
+                int c = (vi < 32) ? __popc(blo & (0xffffffffu >> (31 - vi)))
+                                  : __popc(blo) + __popc(bhi & (0xffffffffu >> (63 - vi)));
+                return (double)c;
+            };
+            cum0 = pref(a); cum1 = pref(bb);
+        }
+    } else if (level == 2) {
+        if constexpr (NARROW) cum0 = (double)(lane + 1);
+        else { cum0 = (double)(2 * lane + 1); cum1 = (double)(2 * lane + 2); }
+    }
+
+    // ---- write the tables -----------------------------------------------------------------------
+    u32* rp = w.rowptr + nb + g;
+    for (int v = lane; v <= n; v += 32) rp[v] = s.rowptr[v];
+    for (int p = lane; p < nnz; p += 32) w.csr_idx[csr_base + p] = (i32)s.idx[p];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const int v = lane + 32 * h;
+        if (v < n) {
+            w.order[nb + v] = s.order[v];
+            w.index_of[nb + v] = s.index_of[v];
+            w.suffix_deg[nb + v] = s.sd[v];
+            w.bucket_b[nb + v] = s.b[v];
+            w.adj[nb + v] = s.adj[v];
+            w.suf[nb + v] = s.suf[v];
+        }
+    }
+    if constexpr (NARROW) {
+        if (lane < n) w.cum[nb + lane] = cum0;
+    } else {
+        if (2 * lane < n) w.cum[nb + 2 * lane] = cum0;
+        if (2 * lane + 1 < n) w.cum[nb + 2 * lane + 1] = cum1;
+    }
+    if (lane == 0) {
+        ugs_ginfo gi;
+        gi.Z = Z; gi.nnz = nnz; gi.level = level;
+        gi.n_eligible = (level == 0) ? n0 : (level == 1 ? n1 : n);
+        gi.last_viable = lastv; gi.mult = mult; gi.cls = 1;
+        w.ginfo[g] = gi;
+    }
+}
+
 #ifndef PRE_MINB
 #define PRE_MINB 6  // min resident CTAs per SM asked of the compiler: 40 registers, 48 warps/SM (B200 A/B: 5 -> 0.389 ms,
 #endif              // 6 -> 0.373 ms, 7 -> 0.405 ms with spills)
@@ -220,194 +440,11 @@ k_preproc_small(const i64* __restrict__ row0, const i64* __restrict__ row1, cons
     }
     // s.deg[v] is the multigraph degree again.
 
-    // ---- A.3 order = stable sort by (degree, id): a counting sort over the DISTINCT degree values (a molecule has four
-    //      or five of them): per value two ballots give every vertex of that degree its rank, ids ascending because
-    //      lane order is id order (vertices lane and lane + 32).
-    {
-        const u32 none = 0xFFFFFFFFu;
-        const u32 d0 = (lane < n) ? s.deg[lane] : none, d1 = (lane + 32 < n) ? s.deg[lane + 32] : none;
-        int base = 0;
-        u32 cur = 0;
-        bool first = true;
-        while (base < n) {
-            const u32 c0 = (d0 != none && (first || d0 > cur)) ? d0 : none;
-            const u32 c1 = (d1 != none && (first || d1 > cur)) ? d1 : none;
-            const u32 mn = __reduce_min_sync(FULL_MASK, min(c0, c1));
-            const u32 b0 = __ballot_sync(FULL_MASK, d0 == mn), b1 = __ballot_sync(FULL_MASK, d1 == mn);
-            if (d0 == mn) {
-                const int rank = base + __popc(b0 & lt_mask);
-                s.order[rank] = (unsigned char)lane;
-                s.index_of[lane] = (unsigned char)rank;
-            }
-            if (d1 == mn) {
-                const int rank = base + __popc(b0) + __popc(b1 & lt_mask);
-                s.order[rank] = (unsigned char)(lane + 32);
-                s.index_of[lane + 32] = (unsigned char)rank;
-            }
-            base += __popc(b0) + __popc(b1);
-            cur = mn;
-            first = false;
-        }
-    }
-    __syncwarp();
-    // ---- suffix masks: suf[vi] = { order[vj] : vj >= vi } ----------------------------------------
-    {
-        u64 xh = (lane + 32 < n) ? (1ull << s.order[lane + 32]) : 0ull;
-        u64 xl = (lane < n) ? (1ull << s.order[lane]) : 0ull;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            u64 yh = __shfl_down_sync(FULL_MASK, xh, off);
-            u64 yl = __shfl_down_sync(FULL_MASK, xl, off);
-            if (lane + off < 32) { xh |= yh; xl |= yl; }
-        }
-        xl |= __shfl_sync(FULL_MASK, xh, 0);
-        s.suf[lane] = xl;
-        s.suf[lane + 32] = xh;
-    }
-    __syncwarp();
-    // ---- A.4 suffix degree, reachability (bounded BFS as a bitmask closure), weight; the same walk over row(v) also
-    //      classifies the row's multiplicities (every neighbour once / twice / both patterns, no self loop) ----------
-    int n0 = 0, n1 = 0, lastv = -1;
-    bool self_or_bad = false;
-    int mu_min = 99, mu_max = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int vi = lane + 32 * h;
-        double b = 0.0;
-        int sd = 0;
-        if (vi < n) {
-            const int v = s.order[vi];
-            const int p0 = s.rowptr[v], p1 = s.rowptr[v + 1];
-            u64 ones = 0, twos = 0, fours = 0;
-            for (int p = p0; p < p1; ++p) {
-                const int x = s.idx[p];
-                sd += (s.index_of[x] >= vi) ? 1 : 0;
-                if (x == v) self_or_bad = true;
-                const u64 bit = 1ull << x;
-                const u64 cy0 = ones & bit; ones ^= bit;
-                const u64 cy1 = twos & cy0; twos ^= cy0;
-                fours |= cy1;
-            }
-            const u64 A = s.adj[v];
-            if (A) {
-                int mu = 0;
-                if (fours) mu = 0;
-                else if (ones == A && twos == 0) mu = 1;
-                else if (twos == A && ones == 0) mu = 2;
-                else if (ones == A && twos == A) mu = 3;
-                if (mu == 0) self_or_bad = true;
-                else { mu_min = min(mu_min, mu); mu_max = max(mu_max, mu); }
-            }
-            const u64 sufm = s.suf[vi];
-            u64 vis = 1ull << v, expd = 0ull;
-            bool reach = false;
-#pragma unroll
-            for (int it = 0; it < (KT ? KT : 16); ++it) {
-                if (it >= k) break;
-                if (__popcll(vis) >= k) { reach = true; break; }
-                const u64 fr = vis & ~expd;
-                if (!fr) break;
-                const int u = __ffsll((long long)fr) - 1;
-                expd |= 1ull << u;
-                vis |= s.adj[u] & sufm;
-            }
-            if (reach) {
-                const double d = (double)(sd > 1 ? sd : 1);
-                b = 1.0;
-#pragma unroll
-                for (int t = 0; t < (KT ? KT - 1 : 15); ++t) {  // preproc.cpp:228-233: k - 1 sequential multiplies
-                    if (t >= k - 1) break;
-                    b *= d;
-                }
-            }
-            if (b > 0.0) { n0++; lastv = vi; }
-            if (sd > 0) n1++;
-        }
-        s.b[vi] = b;
-        s.sd[vi] = (unsigned short)sd;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        n0 += __shfl_xor_sync(FULL_MASK, n0, off);
-        n1 += __shfl_xor_sync(FULL_MASK, n1, off);
-        lastv = max(lastv, __shfl_xor_sync(FULL_MASK, lastv, off));
-        mu_min = min(mu_min, __shfl_xor_sync(FULL_MASK, mu_min, off));
-        mu_max = max(mu_max, __shfl_xor_sync(FULL_MASK, mu_max, off));
-    }
-    self_or_bad = __any_sync(FULL_MASK, self_or_bad);
-    int mult = 0;
-    if (!self_or_bad) mult = (mu_max == 0) ? 1 : (mu_min == mu_max ? mu_min : 0);
-
-    // ---- Z and the root CDF. Every weight is an integer-valued double; if the total is <= 2^53 every
-    //      partial sum is exact, so the parallel prefix equals the reference's left-to-right sum (:234).
-    double cum0, cum1, Z;
-    {
-        const double p0 = s.b[2 * lane], p1 = s.b[2 * lane + 1];
-        double incl = p0 + p1;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            double y = __shfl_up_sync(FULL_MASK, incl, off);
-            if (lane >= off) incl += y;
-        }
-        const double total = __shfl_sync(FULL_MASK, incl, 31);
-        if (total <= 9007199254740992.0) {
-            const double excl = incl - (p0 + p1);
-            cum0 = excl + p0;
-            cum1 = cum0 + p1;
-            Z = total;
-        } else {
-            double run = 0.0;
-            cum0 = cum1 = 0.0;
-            for (int vi = 0; vi < 64; ++vi) {  // sequential, identical on every lane
-                run += s.b[vi];
-                if (vi == 2 * lane) cum0 = run;
-                if (vi == 2 * lane + 1) cum1 = run;
-            }
-            Z = run;
-        }
-    }
-    const int level = (n0 > 0) ? 0 : ((n1 > 0) ? 1 : 2);
-    if (level == 1) {
-        const u32 blo = __ballot_sync(FULL_MASK, s.sd[lane] > 0);
-        const u32 bhi = __ballot_sync(FULL_MASK, s.sd[lane + 32] > 0);
-        // positions 2*lane and 2*lane+1
-        const int a = 2 * lane, bb = 2 * lane + 1;
-        auto pref = [&](int vi) -> double {
-            int c = (vi < 32) ? __popc(blo & (0xffffffffu >> (31 - vi)))
-                              : __popc(blo) + __popc(bhi & (0xffffffffu >> (63 - vi)));
-            return (double)c;
-        };
-        cum0 = pref(a); cum1 = pref(bb);
-    } else if (level == 2) {
-        cum0 = (double)(2 * lane + 1); cum1 = (double)(2 * lane + 2);
-    }
-
-    // ---- write the tables -----------------------------------------------------------------------
-    u32* rp = w.rowptr + nb + g;
-    for (int v = lane; v <= n; v += 32) rp[v] = s.rowptr[v];
-    for (int p = lane; p < nnz; p += 32) w.csr_idx[csr_base + p] = (i32)s.idx[p];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < n) {
-            w.order[nb + v] = s.order[v];
-            w.index_of[nb + v] = s.index_of[v];
-            w.suffix_deg[nb + v] = s.sd[v];
-            w.bucket_b[nb + v] = s.b[v];
-            w.adj[nb + v] = s.adj[v];
-            w.suf[nb + v] = s.suf[v];
-        }
-    }
-    if (2 * lane < n) w.cum[nb + 2 * lane] = cum0;
-    if (2 * lane + 1 < n) w.cum[nb + 2 * lane + 1] = cum1;
-    if (lane == 0) {
-        ugs_ginfo gi;
-        gi.Z = Z; gi.nnz = nnz; gi.level = level;
-        gi.n_eligible = (level == 0) ? n0 : (level == 1 ? n1 : n);
-        gi.last_viable = lastv; gi.mult = mult; gi.cls = 1;
-        w.ginfo[g] = gi;
-    }
+    // everything after the CSR: order, suffix masks, suffix degrees, reachability, weights, CDF, table stores. Graphs of
+    // at most 32 vertices (all of ZINC / QM9 but a handful) take the 32-bit instantiation: one vertex per lane, every mask
+    // operation a single instruction, half the shuffles.
+    if (n <= 32) preproc_small_tail<KT, u32>(s, n, k, nnz, nb, g, csr_base, w);
+    else preproc_small_tail<KT, u64>(s, n, k, nnz, nb, g, csr_base, w);
 }
 
 // =====================================================================================================
