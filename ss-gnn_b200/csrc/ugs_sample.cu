@@ -418,7 +418,8 @@ k_sample_small_pipe(const i64* __restrict__ ptr, int G, i64 node_base, i64 m, in
 }
 
 // m <= 16 samples per graph (QM9-style completeness runs: m = 10) leave most lanes of a (graph, 32-sample tile) warp
-// idle, so a warp takes 32 / S graphs at once, S = 8 or 16 lanes each: every lane group stages the tables of its own
+// idle, so a warp takes 32 / S graphs at once, S = 8, 10 or 16 lanes each (m = 10, the QM9 configuration: three graphs
+// per warp, lanes 30 and 31 idle): every lane group stages the tables of its own
 // graph and samples it. Graphs that need their CSR rows for the entry count (irregular multiplicities, self loops) do
 // not fit this layout: a warp that holds one handles its graphs one after the other with the code above.
 template <int KT, int S>
@@ -439,7 +440,7 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
     const i64 g_first = ((i64)blockIdx.x * SAMP_WARPS + warp) * GPW;
     if (g_first >= G) return;
     const i64 g = g_first + slot;
-    const bool valid = g < G;
+    const bool valid = slot < GPW && g < G;  // S = 10: lanes 30 and 31 belong to no graph
     ugs_ginfo gi;
     gi.cls = -1; gi.mult = 0; gi.level = 0; gi.Z = 0.0; gi.nnz = 0; gi.n_eligible = 0; gi.last_viable = 0;
     if (valid) gi = w.ginfo[g];
@@ -455,7 +456,7 @@ k_sample_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, 
         sample_ptr[g + 1] = (g + 1) * m;  // ugs_sampler_batch_extension.cpp:130
         if (g == 0) { sample_ptr[0] = 0; edge_ptr[0] = 0; }
     }
-    SlotSamp& s = reinterpret_cast<SlotSamp*>(raw[warp])[slot];
+    SlotSamp& s = reinterpret_cast<SlotSamp*>(raw[warp])[valid ? slot : 0];
     const bool live = valid && gi.cls == 1;
     const i64 lo = valid ? ptr[g] : 0;
     const int n = live ? (int)(ptr[g + 1] - lo) : 0;
@@ -1282,7 +1283,7 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                              out_src, packed);
 }
 
-// m <= 16 (QM9-style runs): 32 / S graphs per warp, S = 8 or 16 lanes each, like k_sample_small_packed. Every lane group
+// m <= 16 (QM9-style runs): 32 / S graphs per warp, S = 8, 10 or 16 lanes each, like k_sample_small_packed. Every lane group
 // stages the CSR of its own graph (at most PK_ENT entries; payload = source column relative to the FIRST graph of the
 // warp, 10 bits); the output of the warp's graphs is one contiguous run, so staging and the coalesced flush work as in
 // the one-graph kernel. k <= 8, mode "sample" / encoder, graph-contiguous columns, rows packed by the sampling kernel.
@@ -1318,7 +1319,8 @@ k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, in
     if (g_first >= G) return;
     const i64 g_end = min(G, g_first + GPW);
     const i64 g = g_first + slot;
-    const bool valid = g < G;
+    const bool valid = slot < GPW && g < G;  // S = 10: lanes 30 and 31 belong to no graph
+    const int vslot = valid ? slot : 0;
     ugs_ginfo gi;
     gi.cls = -1; gi.nnz = 0; gi.mult = 0; gi.level = 0; gi.Z = 0.0; gi.n_eligible = 0; gi.last_viable = 0;
     if (valid) gi = w.ginfo[g];
@@ -1342,9 +1344,9 @@ k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, in
         const u32* rp = w.rowptr + (lo - node_base) + g;
         const i32* ci = w.csr_idx + 2 * cg;
         const i32* gc = w.csr_col + 2 * cg;
-        for (int v = i; v < n; v += S) s.rowrange[slot][v] = (rp[v] << 1) | (rp[v + 1] << 17);
+        for (int v = i; v < n; v += S) s.rowrange[vslot][v] = (rp[v] << 1) | (rp[v + 1] << 17);
         const int nnz = live ? gi.nnz : 0;
-        for (int p = i; p < nnz; p += S) s.ent[slot][p] = (unsigned short)((u32)ci[p] | ((u32)(gc[p] - (i32)c0) << 6));
+        for (int p = i; p < nnz; p += S) s.ent[vslot][p] = (unsigned short)((u32)ci[p] | ((u32)(gc[p] - (i32)c0) << 6));
         u32* row = reinterpret_cast<u32*>(&s.lmap[lane][0]);
 #pragma unroll
         for (int q = 0; q < NIB_STRIDE / 4; ++q) row[q] = 0xFFFFFFFFu;
@@ -1358,8 +1360,8 @@ k_emit_small_packed(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, in
     const i64 my_end = has ? edge_ptr[rowid + 1] : my_lo;
     const bool walk = has && live && (my_end > my_lo);
     unsigned char* lrow = &s.lmap[lane][0];
-    const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent[slot]);
-    const u32* rr_tab = s.rowrange[slot];
+    const unsigned char* entb = reinterpret_cast<const unsigned char*>(s.ent[vslot]);
+    const u32* rr_tab = s.rowrange[vslot];
     u32 nb2[2] = {~0u, ~0u};
     if (walk) {
         const u64 prow = packed[rowid];
@@ -1584,6 +1586,9 @@ int ugs_run_scan(i64* edge_ptr, i64 B, void* scratch, size_t scratch_bytes, WS& 
 // A warp handles up to 4 tiles of 32 samples of one graph (the graph's tables are staged once per warp). Small batches
 // do not have enough (graph, 4-tile) items to fill the GPU -- MUTAG-shaped G=188, m=64: 188 warps on 148 SMs -- so
 // they get fewer tiles per warp until there are at least two 8-warp CTAs per SM.
+// lanes per graph of the packed kernels (m <= 16): 4, 3 or 2 graphs per warp
+static inline int packed_lanes(int64_t m) { return m <= 8 ? 8 : (m <= 10 ? 10 : 16); }
+
 static inline void small_items(int64_t m, int64_t G, int* tiles_per_item, int64_t* items_per_graph) {
     const int64_t ntiles = (m + 31) / 32;
     int tpi = (int)(ntiles < 4 ? (ntiles < 1 ? 1 : ntiles) : 4);
@@ -1666,8 +1671,8 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
     if (k <= 8 && scratch && scratch_bytes >= ugs_sample_scratch_bytes(G, m))
         packed = reinterpret_cast<u64*>((char*)scratch + packed_rows_offset(G * m));
     if (m <= 16) {
-        // several graphs per warp: 8 lanes per graph up to m = 8, 16 lanes up to m = 16
-        const int S = m <= 8 ? 8 : 16;
+        // several graphs per warp: 8 lanes per graph up to m = 8, 10 lanes up to m = 10 (three graphs), 16 lanes up to m = 16
+        const int S = packed_lanes(m);
         const int64_t warps = (G + 32 / S - 1) / (32 / S);
         const unsigned grid = (unsigned)((warps + SAMP_WARPS - 1) / SAMP_WARPS);
         const size_t slice = (sizeof(SlotSamp) * (32 / S) > sizeof(SmallSamp)) ? sizeof(SlotSamp) * (32 / S) : sizeof(SmallSamp);
@@ -1680,6 +1685,12 @@ int ugs_sample_batch_impl(const int64_t* ptr, int64_t G, int64_t node_base, int6
             k_sample_small_packed<KT_, 8><<<grid, SAMP_WARPS * 32, psmem, st>>>(ptr, G, node_base, m, k, seed,          \
                                                                                  graph_index_base, ibase, seed_mode, w, \
                                                                                  nodes, edge_ptr, sample_ptr, packed); \
+        } else if (S == 10) {                                                                                           \
+            UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_small_packed<KT_, 10>,                                         \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
+            k_sample_small_packed<KT_, 10><<<grid, SAMP_WARPS * 32, psmem, st>>>(ptr, G, node_base, m, k, seed,         \
+                                                                                  graph_index_base, ibase, seed_mode, w, \
+                                                                                  nodes, edge_ptr, sample_ptr, packed); \
         } else {                                                                                                        \
             UGS_CUDA_CHECK(cudaFuncSetAttribute(k_sample_small_packed<KT_, 16>,                                         \
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
@@ -1842,10 +1853,15 @@ int ugs_emit_edges_impl(const int64_t* ptr, int64_t G, int64_t node_base, int64_
         const unsigned grid = (unsigned)((items + EMIT_WARPS - 1) / EMIT_WARPS);
         if (k <= 8 && (mode == UGS_MODE_SAMPLE || mode == UGS_MODE_ENCODER) && m <= 16 && packed && !use_perm) {
             // several graphs per warp (the rows must be the packed ones ugs_sample_batch left behind)
-            const int S = m <= 8 ? 8 : 16;
+            const int S = packed_lanes(m);
             const int64_t warps = (G + 32 / S - 1) / (32 / S);
             const unsigned pgrid = (unsigned)((warps + EMIT_WARPS - 1) / EMIT_WARPS);
-            if (S == 8) {
+            if (S == 10) {
+                const size_t sl = sizeof(PackedEmit<3>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<3>) : sizeof(SmallEmit<unsigned short>);
+                UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
+                k_emit_small_packed<10><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,
+                                                                                        out_u, out_v, edge_src_out, packed, flags);
+            } else if (S == 8) {
                 const size_t sl = sizeof(PackedEmit<4>) > sizeof(SmallEmit<unsigned short>) ? sizeof(PackedEmit<4>) : sizeof(SmallEmit<unsigned short>);
                 UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small_packed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sl * EMIT_WARPS)));
                 k_emit_small_packed<8><<<pgrid, EMIT_WARPS * 32, sl * EMIT_WARPS, st>>>(ptr, G, node_base, m, k, mode, w, nodes, edge_ptr,

@@ -364,3 +364,26 @@ def test_many_general_path_samples_take_the_thread_per_sample_kernel(cuda_lib, k
             assert np.array_equal(a.cpu().numpy(), r), (name, mode)
         assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
         assert stats["n_edge_entries"] == ref[1].shape[1]
+
+
+@pytest.mark.parametrize("k,m", [(8, 64), (4, 40), (5, 33)])
+def test_large_batch_takes_the_pipelined_sampling_kernel(cuda_lib, k, m):
+    """Batches with at least two graphs per resident warp (>= 2 x 148 SMs x 4 CTAs x 8 warps = 9472 graphs) and every tile of
+    a graph in one work item are sampled by k_sample_small_pipe (persistent warps, cp.async fetch-ahead of the next graph's
+    tables). Every kind of graph between the molecules -- multi-edges / self loops (CSR rows staged when the graph's turn
+    comes), graphs smaller than k, graphs above 32 vertices (64-bit masks) and above 64 (general path, skipped by this
+    kernel) -- all five outputs bit-exact against the oracle."""
+    from ugs_b200 import synth
+    rng = np.random.default_rng(1000 + k)
+    parts = []
+    for i in range(6):
+        parts.append(synth.make_batch("zinc" if i % 2 else "qm9", 1990, seed=10 * k + i))
+        parts.append(random_batch(rng, 30, 1, 45, deg=2.5, weird=True, big=[(3, 120), (17, 70)]))
+    ei, ptr = synth.concat_batches(parts)
+    assert len(ptr) - 1 >= 12000
+    b = _batch(ei, ptr, k)
+    outs, stats = b.sample(m, k, "sample", seed=5)
+    ref = _oracle_batch(ei, ptr, m, k, "sample", 5)
+    for name, a, r in zip(["nodes", "edge_index", "edge_ptr", "sample_ptr", "edge_src"], outs, ref):
+        assert np.array_equal(a.cpu().numpy(), r), name
+    assert stats["n_incomplete"] == int((ref[0] < 0).any(axis=1).sum()) - m * stats["n_skipped_graphs"]
