@@ -292,12 +292,36 @@ extern "C" size_t ugs_deliver_wire_bytes(int64_t B, int k, int64_t total, int pa
     return ugs_wire_layout((size_t)B * k, (size_t)total, (size_t)total, pairs_u8, 0).total;
 }
 
+// prepacked: the edge part of d_wire (one byte per entry, 16-bit source-column deltas and their block bases) was written
+// by ugs_emit_edges_wire; only the node ids are packed here. No DMA share, no int32 fallback: a value that does not fit
+// is reported as UGS_ELIMIT and the caller takes the int64 path.
+static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index, const int64_t* edge_src,
+                        int64_t total, int pairs_u8, double dma_fraction, void* d_wire, void* h_wire, size_t wire_bytes,
+                        int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, int64_t* h_stats,
+                        void* stream_, int prepacked);
+
 extern "C" int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index,
                                    const int64_t* edge_src, int64_t total, int pairs_u8, double dma_fraction,
                                    void* d_wire, void* h_wire, size_t wire_bytes, int64_t* h_nodes, int64_t* h_edge_index,
                                    int64_t* h_edge_src, int n_threads, int64_t* h_stats, void* stream_) {
+    return deliver_impl(nodes, B, k, edge_index, edge_src, total, pairs_u8, dma_fraction, d_wire, h_wire, wire_bytes, h_nodes,
+                        h_edge_index, h_edge_src, n_threads, h_stats, stream_, 0);
+}
+
+extern "C" int ugs_deliver_outputs_wire(const int64_t* nodes, int64_t B, int k, int64_t total, void* d_wire, void* h_wire,
+                                        size_t wire_bytes, int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src,
+                                        int n_threads, int64_t* h_stats, void* stream_) {
+    return deliver_impl(nodes, B, k, nullptr, nullptr, total, 1, 0.0, d_wire, h_wire, wire_bytes, h_nodes, h_edge_index,
+                        h_edge_src, n_threads, h_stats, stream_, 1);
+}
+
+static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* edge_index, const int64_t* edge_src,
+                        int64_t total, int pairs_u8, double dma_fraction, void* d_wire, void* h_wire, size_t wire_bytes,
+                        int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src, int n_threads, int64_t* h_stats,
+                        void* stream_, int prepacked) {
     if (B < 0 || total < 0 || k < 1) return ugs_set_error(UGS_EINVAL, "bad size");
-    if ((B * k > 0 && (!nodes || !h_nodes)) || (total > 0 && (!edge_index || !edge_src || !h_edge_index || !h_edge_src)))
+    if ((B * k > 0 && (!nodes || !h_nodes)) ||
+        (total > 0 && ((!prepacked && (!edge_index || !edge_src)) || !h_edge_index || !h_edge_src)))
         return ugs_set_error(UGS_EINVAL, "NULL array");
     cudaStream_t st = (cudaStream_t)stream_;
     int rc = UGS_OK, dev = 0;
@@ -350,7 +374,8 @@ extern "C" int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const
     };
     // ---- widen pipeline -----------------------------------------------------------------------------------------------
     if (pn + pe + pi > 0) {
-        rc = ugs_pack_parts(nodes + sn, pn, edge_index + si, edge_index + NE + si, pi, edge_src + se, pe, pairs_u8, 1, dw, &w, st);
+        if (prepacked) rc = ugs_pack_parts(nodes, pn, nullptr, nullptr, 0, nullptr, 0, 1, 1, dw, &w, st);
+        else rc = ugs_pack_parts(nodes + sn, pn, edge_index + si, edge_index + NE + si, pi, edge_src + se, pe, pairs_u8, 1, dw, &w, st);
         if (rc != UGS_OK) goto out;
         // block minima + the overflow counters first: they decide the format and every widening thread needs the minima
         CK(cudaMemcpyAsync(hw + w.nodes_base, dw + w.nodes_base, w.total - w.nodes_base, cudaMemcpyDeviceToHost, st));
@@ -358,6 +383,10 @@ extern "C" int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const
         {
             const unsigned long long* bad = (const unsigned long long*)(hw + w.bad);
             if (bad[1]) { rc = ugs_set_error(UGS_ELIMIT, "%llu edge entries do not fit the packed wire format", bad[1]); goto out; }
+            if (prepacked && (bad[0] | bad[2])) {
+                rc = ugs_set_error(UGS_ELIMIT, "%llu node ids / %llu source columns do not fit a 16-bit delta", bad[0], bad[2]);
+                goto out;
+            }
             if (bad[0]) {  // some 4096-value block spreads over more than 65534: int32 for node ids / source columns
                 delta16 = 0;
                 w = ugs_wire_layout(pn, pe, pi, pairs_u8, 0);

@@ -9,6 +9,7 @@
 // Both paths draw the same Philox words and pick the r-th smallest vertex id of the distinct cut, so they
 // (and oracle/ugs_oracle.c) produce identical samples.
 #include "ugs_common.cuh"
+#include "ugs_hostio.h"
 
 #define SAMP_WARPS 8
 // Measured on B200 (profiles/README.md, A/B of the ZINC-shaped step): 4 resident CTAs (64 registers, 32 bytes of
@@ -1034,12 +1035,22 @@ struct __align__(16) SmallEmit<unsigned short> {  // 5664 bytes per warp: 5 CTAs
 // NARROW: k <= 8 and mode "sample" / encoder: staged entry = payload << 6 | l << 3 | j  (16 bits)
 // else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
 // Entries of the samples of tiles [t0, t1) of graph g, by one warp whose shared-memory slice is `s`.
-template <bool NARROW>
+// WIRE (host delivery, ugs_emit_edges_wire): the flush writes the transfer format of csrc/ugs_hostio.h directly instead
+// of three int64 arrays -- one byte (j | l << 4) per entry and the source column as a 16-bit delta against bases[] of its
+// 4096-entry block (k_wire_src_bases) -- 3 instead of 24 bytes per entry, and no int64 copy of the edges in HBM at all.
+struct WireOut {
+    unsigned char* ei;
+    unsigned short* src;
+    const i64* bases;
+    unsigned long long* bad;  // entries whose delta does not fit 16 bits (the caller falls back to the int64 path)
+};
+
+template <bool NARROW, bool WIRE = false>
 __device__ __forceinline__ void emit_graph_tiles(
     SmallEmit<typename std::conditional<NARROW, unsigned short, u32>::type>& s, i64 g, int t0, int t1,
     const i64* __restrict__ ptr, i64 node_base, i64 m, int k, int mode, int use_perm, const WS& w,
     const i64* __restrict__ nodes, const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-    i64* __restrict__ out_src, const u64* __restrict__ packed) {
+    i64* __restrict__ out_src, const u64* __restrict__ packed, WireOut wo = WireOut()) {
     typedef typename std::conditional<NARROW, unsigned short, u32>::type stage_t;
     constexpr bool NIBBLE = NARROW && (EMIT_NIBBLE != 0);  // k <= 8: two vertices per lmap byte
     constexpr int STAGE_N = (int)(sizeof(SmallEmit<stage_t>::stage) / sizeof(stage_t));
@@ -1198,6 +1209,23 @@ __device__ __forceinline__ void emit_graph_tiles(
                     }
                     pu += 32; pv += 32; ps += 32; sg += 32;
                 }
+            } else if (NARROW && WIRE) {
+                // a run (<= NIB_STAGE entries) touches at most two 4096-entry blocks
+                const i64 blk0 = base >> 12;
+                const int split = (int)(((blk0 + 1) << 12) - base);  // entries [split, run) belong to block blk0 + 1
+                const i64 rel0 = c0 - wo.bases[blk0];
+                const i64 rel1 = (split < run) ? c0 - wo.bases[blk0 + 1] : rel0;
+                unsigned char* pe8 = wo.ei + base;
+                unsigned short* ps16 = wo.src + base;
+                int nbad = 0;
+                for (int e = lane; e < run; e += 32) {
+                    const u32 pk = s.stage[e];
+                    pe8[e] = (unsigned char)((pk & 7u) | (((pk >> 3) & 7u) << 4));
+                    const i64 d = (e < split ? rel0 : rel1) + (i64)(pk >> 6);
+                    if (d < 0 || d >= 0xFFFF) nbad++;
+                    ps16[e] = (unsigned short)d;
+                }
+                if (nbad) atomicAdd(wo.bad, (unsigned long long)nbad);
             } else if (NARROW) {
                 i64* pu = out_u + base + lane;
                 i64* pv = out_v + base + lane;
@@ -1256,12 +1284,12 @@ __device__ __forceinline__ void emit_graph_tiles(
     }
 }
 
-template <bool NARROW>
+template <bool NARROW, bool WIRE = false>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, NARROW ? EMIT_MINB : 3)
 k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, int mode, int tiles_per_item,
              i64 items_per_graph, int use_perm, WS w, const i64* __restrict__ nodes,
              const i64* __restrict__ edge_ptr, i64* __restrict__ out_u, i64* __restrict__ out_v,
-             i64* __restrict__ out_src, const u64* __restrict__ packed, int flags) {
+             i64* __restrict__ out_src, const u64* __restrict__ packed, int flags, WireOut wo = WireOut()) {
     // fused path queued on the guess "no general-path graph": a wrong guess leaves garbage offsets, write nothing then
     if ((flags & UGS_EMIT_GUARD_GENERAL) && w.counters[UGS_CTR_N_GENERAL] != 0) return;
     if (flags & UGS_EMIT_COMPACT) {  // rows packed behind one another at the total the scan kernel left on the device
@@ -1279,8 +1307,24 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
     const int chunk = (int)(item - g * items_per_graph);
     const int ntiles = (int)((m + 31) >> 5);
     const int t0 = chunk * tiles_per_item, t1 = min(ntiles, t0 + tiles_per_item);
-    emit_graph_tiles<NARROW>(sm_all[warp], g, t0, t1, ptr, node_base, m, k, mode, use_perm, w, nodes, edge_ptr, out_u, out_v,
-                             out_src, packed);
+    emit_graph_tiles<NARROW, WIRE>(sm_all[warp], g, t0, t1, ptr, node_base, m, k, mode, use_perm, w, nodes, edge_ptr, out_u,
+                                   out_v, out_src, packed, wo);
+}
+
+// bases[b] for the 16-bit source-column deltas of block b (entries [4096 b, 4096 b + 4096) of the output): the first
+// column of the graph that owns the block's first entry. Every later entry of the block belongs to the same or a later
+// graph, so its source column is >= that base; k_emit_small<true, true> counts the entries whose delta exceeds 16 bits.
+__global__ void k_wire_src_bases(const i64* __restrict__ edge_ptr, i64 B, i64 m, i64 total, const i64* __restrict__ cstart,
+                                 i64* __restrict__ bases) {
+    const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 pos = b << 12;
+    if (pos >= total) return;
+    i64 lo = 0, hi = B;  // the last sample s with edge_ptr[s] <= pos (edge_ptr[0] = 0, edge_ptr[B] = total > pos)
+    while (hi - lo > 1) {
+        const i64 mid = (lo + hi) >> 1;
+        if (edge_ptr[mid] <= pos) lo = mid; else hi = mid;
+    }
+    bases[b] = cstart[lo / m];
 }
 
 // m <= 16 (QM9-style runs): 32 / S graphs per warp, S = 8, 10 or 16 lanes each, like k_sample_small_packed. Every lane group
@@ -1824,6 +1868,41 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
                                      size_t sample_scratch_bytes, void* stream_) {
     return ugs_emit_edges_impl(ptr, G, node_base, m, k, mode, use_perm, n_general, workspace, L, nodes, edge_ptr, total,
                                edge_index_out, edge_src_out, sample_scratch, sample_scratch_bytes, 0, stream_);
+}
+
+extern "C" int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k,
+                                   const void* workspace, const ugs_layout* L, const int64_t* nodes,
+                                   const int64_t* edge_ptr, int64_t total, void* d_wire, size_t wire_bytes,
+                                   const void* sample_scratch, size_t sample_scratch_bytes, void* stream_) {
+    if (!workspace || !L || !edge_ptr || !nodes || !d_wire) return ugs_set_error(UGS_EINVAL, "NULL argument");
+    if (k < 1 || k > 8) return ugs_set_error(UGS_ELIMIT, "the wire emission needs k <= 8");
+    if (G <= 0 || m <= 0 || total <= 0) return UGS_OK;
+    const UgsWire wl = ugs_wire_layout((size_t)(G * m) * (size_t)k, (size_t)total, (size_t)total, 1, 1);
+    if (wire_bytes < wl.total) return ugs_set_error(UGS_EINVAL, "wire buffer too small");
+    cudaStream_t st = (cudaStream_t)stream_;
+    WS w = ws_views(const_cast<void*>(workspace), L);
+    char* base = (char*)d_wire;
+    WireOut wo;
+    wo.ei = (unsigned char*)(base + wl.ei);
+    wo.src = (unsigned short*)(base + wl.src);
+    wo.bases = (const i64*)(base + wl.src_base);
+    wo.bad = (unsigned long long*)(base + wl.bad) + 2;  // behind the two counters of ugs_pack_parts
+    UGS_CUDA_CHECK(cudaMemsetAsync(wo.bad, 0, 8, st));
+    const u64* packed = nullptr;
+    if (sample_scratch && sample_scratch_bytes >= ugs_sample_scratch_bytes(G, m))
+        packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
+    const int64_t nblk = (total + 4095) >> 12;
+    k_wire_src_bases<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(edge_ptr, G * m, m, total, w.cstart, (i64*)(base + wl.src_base));
+    UGS_LAUNCH_CHECK("k_wire_src_bases");
+    int tpi; int64_t ipg;
+    small_items(m, G, &tpi, &ipg);
+    const unsigned grid = (unsigned)((G * ipg + EMIT_WARPS - 1) / EMIT_WARPS);
+    const size_t smem = sizeof(SmallEmit<unsigned short>) * EMIT_WARPS;
+    UGS_CUDA_CHECK(cudaFuncSetAttribute(k_emit_small<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_emit_small<true, true><<<grid, EMIT_WARPS * 32, smem, st>>>(ptr, G, node_base, m, k, UGS_MODE_SAMPLE, tpi, ipg, 0, w, nodes,
+                                                                  edge_ptr, nullptr, nullptr, nullptr, packed, 0, wo);
+    UGS_LAUNCH_CHECK("k_emit_small_wire");
+    return UGS_OK;
 }
 
 // flags: UGS_EMIT_GUARD_GENERAL / UGS_EMIT_COMPACT (ugs_common.cuh), set by the fused small-batch path only

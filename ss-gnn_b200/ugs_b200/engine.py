@@ -197,7 +197,7 @@ class DeviceBatch:
     # ------------------------------------------------------------------------------------------------
     def sample(self, m: int, k: int | None = None, mode: str = "sample", seed: int = 42,
                graph_index_base: int = 0, variant: str | None = None, emit: bool = True,
-               sample_index_base: int = 0, per_graph_seed: bool = False):
+               sample_index_base: int = 0, per_graph_seed: bool = False, alloc_edges: bool = True):
         """Returns device tensors (nodes[G*m,k], edge_index[2,Ebar], edge_ptr[G*m+1], sample_ptr[G+1],
         edge_src[Ebar]) and the stats dict. One host sync (reading Ebar) between sampling and emission."""
         L = _lib.lib()
@@ -235,7 +235,7 @@ class DeviceBatch:
                 info = self.info()
             if self._late_check(info):
                 return self.sample(m, k, mode, seed, graph_index_base, variant, emit, sample_index_base,
-                                   per_graph_seed)
+                                   per_graph_seed, alloc_edges)
             if info[CTR["unsorted"]] & 16:
                 raise RuntimeError(f"k={k} exceeds the bitmask path's limit of 16 for a batch preprocessed for k={self.k}")
             total = info[CTR["total_edges"]]
@@ -245,8 +245,9 @@ class DeviceBatch:
             stats = dict(n_graphlets=G * m, n_edge_entries=total, n_incomplete=info[CTR["incomplete"]],
                          n_relaxed_graphs=info[CTR["relaxed"]], n_skipped_graphs=self.n_skipped,
                          n_general_graphs=self.n_general, n_trials=n_trials)
-            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev)
-            edge_src = torch.empty(total, dtype=torch.int64, device=dev)
+            # alloc_edges=False (with emit=False): the caller decides between emit_last and emit_last_wire first
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=dev) if (alloc_edges or emit) else None
+            edge_src = torch.empty(total, dtype=torch.int64, device=dev) if (alloc_edges or emit) else None
             # only the reference-law kernels leave packed rows behind the scan words of `scratch`
             packed = scratch if variant == "ref" else None
             self._emit_args = (nodes, edge_ptr, total, m, k, edge_index, edge_src, packed, sbytes)
@@ -254,11 +255,33 @@ class DeviceBatch:
                 self.emit_last(mode)
         return (nodes, edge_index, edge_ptr, sample_ptr, edge_src), stats
 
+    def wire_eligible(self, mode: str) -> bool:
+        """True if the rows of the last `sample(..., emit=False)` call can be emitted in the host-transfer format
+        (`emit_last_wire`): mode "sample", k <= 8, graph-contiguous columns, no general-path graph, reference law."""
+        a = self._emit_args
+        return (a is not None and mode == "sample" and a[4] <= 8 and self.perm is None and self.n_general == 0
+                and a[7] is not None and a[2] > 0)
+
+    def emit_last_wire(self, d_wire: torch.Tensor):
+        """Induced-edge emission of the last `sample(..., emit=False)` call straight into the transfer format of the host
+        delivery (csrc/ugs_hostio.h): d_wire holds >= ugs_deliver_wire_bytes(G*m, k, total, 1) bytes. The int64 edge
+        arrays are never materialised in HBM; `ugs_deliver_outputs_wire` finishes the job."""
+        nodes, edge_ptr, total, m, k, _ei, _es, scratch, sbytes = self._emit_args
+        G = max(self.G, 0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ugs_emit_edges_wire(
+                _ptr(self.ptr), G, self.node_base, m, k, _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes),
+                _ptr(edge_ptr), total, _ptr(d_wire), int(d_wire.numel()), _ptr(scratch), sbytes, _stream()))
+
     def emit_last(self, mode: str = "sample"):
         """Induced-edge emission for the rows of the last `sample(..., emit=False)` call (bench.py times the two halves
         separately). Uses the packed rows that call left in its scratch buffer."""
         nodes, edge_ptr, total, m, k, edge_index, edge_src, scratch, sbytes = self._emit_args
         G = max(self.G, 0)
+        if edge_index is None:  # sample(..., alloc_edges=False)
+            edge_index = torch.empty((2, total), dtype=torch.int64, device=self.device)
+            edge_src = torch.empty(total, dtype=torch.int64, device=self.device)
+            self._emit_out = (edge_index, edge_src)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ugs_emit_edges_packed(
                 _ptr(self.ptr), G, self.node_base, m, k, MODES[mode], 1 if self.perm is not None else 0, self.n_general,

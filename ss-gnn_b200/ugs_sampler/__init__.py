@@ -139,6 +139,55 @@ def _dma_fraction(threads: int) -> float:
     return 0.0
 
 
+def _wire_emit_wanted(G: int, m: int, k: int, E: int) -> bool:
+    """Large results for a CPU caller: emit the edges in the transfer format (no int64 copy of them in HBM, no packing
+    pass). UGS_B200_WIRE_EMIT=0 keeps the int64 emission + packing; the size test mirrors _PACKED_MIN_BYTES with the
+    input's column count as the estimate of the output's entries per sample."""
+    if os.environ.get("UGS_B200_WIRE_EMIT", "1") == "0" or os.environ.get("UGS_B200_PACKED_D2H", "1") == "0":
+        return False
+    if _dma_fraction(_host_threads()) > 0.0 or m <= 16 or k > 8:
+        return False
+    return 8 * (G * m * k + 3 * m * E) >= _PACKED_MIN_BYTES
+
+
+def _deliver_wire(b, outs, stats, k: int):
+    """Emission into the wire format + copy / widen pipeline for the rows `b.sample(..., emit=False, alloc_edges=False)`
+    left behind. Returns the five pinned CPU tensors, or None when a value does not fit the format (the caller then takes
+    the int64 path)."""
+    import ctypes
+    from ugs_b200 import _lib
+    from ugs_b200.engine import _ptr, _stream
+    nodes, _ei, eptr, sptr, _es = outs
+    L = _lib.lib()
+    B, kk, total = int(nodes.shape[0]), int(nodes.shape[1]), int(stats["n_edge_entries"])
+    dev = nodes.device
+    threads = _host_threads()
+    with torch.cuda.device(dev):
+        wb = int(L.ugs_deliver_wire_bytes(B, kk, total, 1))
+        d_wire = torch.empty(wb, dtype=torch.uint8, device=dev)
+        b.emit_last_wire(d_wire)
+        h_wire = torch.empty(wb, dtype=torch.uint8, pin_memory=True)
+        h_nodes = torch.empty(nodes.shape, dtype=torch.int64, pin_memory=True)
+        h_eidx = torch.empty((2, total), dtype=torch.int64, pin_memory=True)
+        h_esrc = torch.empty(total, dtype=torch.int64, pin_memory=True)
+        h_eptr = torch.empty(eptr.shape, dtype=torch.int64, pin_memory=True)
+        h_sptr = torch.empty(sptr.shape, dtype=torch.int64, pin_memory=True)
+        h_eptr.copy_(eptr, non_blocking=True)
+        h_sptr.copy_(sptr, non_blocking=True)
+        st = (ctypes.c_int64 * 4)()
+        rc = L.ugs_deliver_outputs_wire(_ptr(nodes), B, kk, total, _ptr(d_wire), ctypes.c_void_p(h_wire.data_ptr()), wb,
+                                        ctypes.c_void_p(h_nodes.data_ptr()), ctypes.c_void_p(h_eidx.data_ptr()),
+                                        ctypes.c_void_p(h_esrc.data_ptr()), threads, st, _stream())
+        torch.cuda.current_stream().synchronize()
+        if rc == -3:  # UGS_ELIMIT
+            return None
+        _lib.check(rc)
+    _to_host_batch.last_d2h_bytes = int(st[0]) + 8 * (eptr.numel() + sptr.numel())
+    _to_host_batch.last_delivery = (f"dma_fraction 0.00: 0 B as int64 by DMA + {int(st[0])} B packed (16-bit deltas / u8 pairs, "
+                                    f"edges emitted in the wire format), widened by {threads} host threads")
+    return [h_nodes, h_eidx, h_eptr, h_sptr, h_esrc]
+
+
 def _to_host_batch(outs, mode: str, k: int):
     """The 5-tuple (nodes, edge_index, edge_ptr, sample_ptr, edge_src) as CPU pinned int64 tensors (the reference's
     output contract). Large results are split between a plain int64 DMA and a packed transfer (16-bit deltas / one byte
@@ -301,7 +350,19 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
             _engine._fused_tls.last_buffers = None
         else:
             b = _engine.DeviceBatch(ei, p, int(k), pb[0], NT, variant=variant)
-            r = b.sample(int(m_per_graph), int(k), mode, int(seed))
+            if (variant == "ref" and mode == "sample" and not _want_cuda_out(edge_index) and not _debug_on()
+                    and _wire_emit_wanted(G, int(m_per_graph), int(k), E)):
+                # CPU caller, large result: sample, then emit the edges in the transfer format and deliver them
+                r = b.sample(int(m_per_graph), int(k), mode, int(seed), emit=False, alloc_edges=False)
+                sample_batch.last_stats = r[1]
+                if b.wire_eligible(mode):
+                    host = _deliver_wire(b, r[0], r[1], int(k))
+                    if host is not None:
+                        return tuple(host)
+                b.emit_last(mode)  # the int64 path after all (general-path graphs, unsorted columns, a delta out of range)
+                r = ((r[0][0], b._emit_out[0], r[0][2], r[0][3], b._emit_out[1]), r[1])
+            else:
+                r = b.sample(int(m_per_graph), int(k), mode, int(seed))
             if _debug_on():
                 _debug_report(b, r[0][0], int(m_per_graph), int(k), with_cache_line=True)
         outs, _stats = r
