@@ -16,11 +16,11 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
-def run(wire):
+def run_wire():
     ts = []
     for it in range(12):
         b = DeviceBatch(d_ei, d_ptr, k, 0, NT)
-        outs, st = b.sample(m, k, "sample", seed=it, emit=False, alloc_edges=not wire)
+        outs, st = b.sample(m, k, "sample", seed=it, emit=False, alloc_edges=False)
         nodes, total = outs[0], st["n_edge_entries"]
         B = nodes.shape[0]
         wb = int(L.ugs_deliver_wire_bytes(B, k, total, 1))
@@ -28,11 +28,7 @@ def run(wire):
         flush.zero_()
         a, c = ev(), ev()
         a.record()
-        if wire:
-            b.emit_last_wire(d_wire)
-        else:
-            b.emit_last("sample")
-            L.ugs_pack_for_probe  # noqa: B018 (never reached: see below)
+        b.emit_last_wire(d_wire)
         c.record(); c.synchronize()
         ts.append(a.elapsed_time(c))
     return sorted(ts)[len(ts) // 2]
@@ -59,7 +55,7 @@ def run_int64_and_pack():
     return sorted(ts)[len(ts) // 2], sorted(tp)[len(tp) // 2]
 
 
-t_wire = run(True)
+t_wire = run_wire()
 t_emit, t_pack = run_int64_and_pack()
 print(f"emission in the wire format (k_wire_src_bases + k_emit_small<1,1>): {t_wire:.3f} ms")
 print(f"int64 emission (k_emit_small<1>): {t_emit:.3f} ms; packing traffic as torch ops (upper bound of the pack kernels): {t_pack:.3f} ms")
