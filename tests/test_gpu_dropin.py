@@ -260,6 +260,45 @@ def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+@pytest.mark.parametrize("k,m", [(8, 37), (4, 70), (5, 17)])
+def test_wire_emission_equals_plain_copy(cuda_lib, k, m, monkeypatch):
+    """Large CPU results in mode "sample" with k <= 8: the emission pass writes the host-transfer format itself
+    (ugs_emit_edges_wire: one byte per entry, 16-bit source-column deltas against per-block graph bases) and
+    ugs_deliver_outputs_wire widens it -- bit-identical to the int64 emission + plain copy. Batches with skipped graphs,
+    multi-edges / self loops and graphs above 32 vertices in between; a batch with a general-path graph and
+    UGS_B200_WIRE_EMIT=0 take the int64 emission."""
+    import ugs_sampler
+    from ugs_b200 import synth
+    monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
+    monkeypatch.setattr(ugs_sampler._engine, "fused_eligible", lambda *a: False)  # the staged path, as for large batches
+    rng = np.random.default_rng(3 * k + m)
+    parts = [synth.make_batch("zinc", 1500, seed=k), random_batch(rng, 40, 1, 45, deg=2.5, weird=True),
+             synth.make_batch("qm9", 700, seed=m)]
+    ei, ptr = synth.concat_batches(parts)
+    tei, tptr = torch.from_numpy(ei), torch.from_numpy(ptr)
+    monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+    plain = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
+    monkeypatch.delenv("UGS_B200_PACKED_D2H")
+    wire = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
+    assert "emitted in the wire format" in ugs_sampler._to_host_batch.last_delivery
+    for a, b in zip(wire, plain):
+        assert a.dtype == torch.int64 and a.is_pinned() and torch.equal(a, b)
+    assert ugs_sampler.sample_batch.last_stats["n_edge_entries"] == plain[4].numel()
+    monkeypatch.setenv("UGS_B200_WIRE_EMIT", "0")
+    classic = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
+    assert "emitted in the wire format" not in ugs_sampler._to_host_batch.last_delivery
+    monkeypatch.delenv("UGS_B200_WIRE_EMIT")
+    assert all(torch.equal(a, b) for a, b in zip(classic, plain))
+    # one general-path graph (70 vertices) in the batch: not eligible, the int64 path delivers
+    ei2, ptr2 = synth.concat_batches(parts + [random_batch(rng, 3, 1, 30, deg=2.5, big=[(1, 70)])])
+    monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+    plain2 = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), m, k, "sample", 12)
+    monkeypatch.delenv("UGS_B200_PACKED_D2H")
+    mixed = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), m, k, "sample", 12)
+    assert "emitted in the wire format" not in ugs_sampler._to_host_batch.last_delivery
+    assert all(torch.equal(a, b) for a, b in zip(mixed, plain2))
+
+
 def test_concurrent_calls_from_python_threads(cuda_lib, monkeypatch):
     """ctypes releases the GIL, so two Python threads can be inside libugs_b200 at the same time (the reference holds
     the GIL for the whole call): results must be the ones of the serial calls."""
