@@ -435,6 +435,10 @@ int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_
 int ugs_deliver_outputs_wire(const int64_t* nodes, int64_t B, int k, int64_t total, void* d_wire, void* h_wire,
                              size_t wire_bytes, int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src,
                              int n_threads, int64_t* h_stats, void* stream);
+/* Host-only: copies bytes from src (pageable memory of the caller: the trainer's `.cpu()` tensors, experiment.py:877-878)
+ * to dst (a pinned staging buffer) with n_threads threads of the delivery pool; the H2D copy then runs from pinned
+ * memory at the link rate instead of being staged by the driver on one thread. */
+int ugs_host_copy(void* dst, const void* src, size_t bytes, int n_threads);
 double ugs_host_store_bandwidth(void* dst, size_t bytes, int n_threads, int reps);
 const char* ugs_host_isa(void);
 /* host-only test hook: widen n packed elements with the named code variant ("scalar" | "avx2" | "avx512"; -1 = this CPU

@@ -24,7 +24,7 @@ EXPORTS = [
     "ugs_wl_hash", "ugs_wl_lookup", "ugs_wl_node_attr",
     "ugs_batch_info_begin", "ugs_batch_info_end", "ugs_preproc_batch_parts",
     "ugs_deliver_wire_bytes", "ugs_deliver_outputs", "ugs_host_store_bandwidth", "ugs_host_isa", "ugs_host_widen",
-    "ugs_emit_edges_packed", "ugs_sample_batch_early", "ugs_emit_edges_wire", "ugs_deliver_outputs_wire",
+    "ugs_emit_edges_packed", "ugs_sample_batch_early", "ugs_emit_edges_wire", "ugs_deliver_outputs_wire", "ugs_host_copy",
     "ugs_fused_capacity", "ugs_sample_batch_fused", "ugs_fused_finish",
 ]
 
@@ -144,6 +144,7 @@ def lib():
     L.ugs_deliver_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, cd, vp, vp, sz, vp, vp, vp, ci, vp, vp]
     L.ugs_emit_edges_wire.argtypes = [vp, i64, i64, i64, ci, vp, LP, vp, vp, i64, vp, sz, vp, sz, vp]
     L.ugs_deliver_outputs_wire.argtypes = [vp, i64, ci, i64, vp, vp, sz, vp, vp, vp, ci, vp, vp]
+    L.ugs_host_copy.argtypes = [vp, vp, sz, ci]
     L.ugs_host_store_bandwidth.restype = cd
     L.ugs_host_store_bandwidth.argtypes = [vp, sz, ci, ci]
     L.ugs_host_isa.restype = ctypes.c_char_p

@@ -139,6 +139,39 @@ def _dma_fraction(threads: int) -> float:
     return 0.0
 
 
+# measured on the pool's hosts (profiles/r02_pageable_probe.txt): 105 MB of columns 62.6 -> 59.2 ms per call, 69 MB 10.4 -> 9.3 ms;
+# 10-13 MB are 1.4 ms SLOWER than the driver's own staging, hence the threshold
+_STAGE_MIN_BYTES = 32 << 20
+_stage_tls = threading.local()
+
+
+def _to_device(t: torch.Tensor, dev) -> torch.Tensor:
+    """Host -> device copy of an input tensor. Large PAGEABLE tensors (what the trainer passes) go through a cached pinned
+    staging buffer filled by the delivery's host threads (ugs_host_copy): the driver's own staging of pageable memory
+    runs on one thread at a fraction of the link rate. UGS_B200_STAGE_INPUTS=0 leaves every copy to the driver."""
+    if (t.is_cuda or t.is_pinned() or not t.is_contiguous() or t.numel() * t.element_size() < _STAGE_MIN_BYTES
+            or os.environ.get("UGS_B200_STAGE_INPUTS", "1") == "0"):
+        return t.to(dev, non_blocking=True)
+    from ugs_b200 import _lib
+    nbytes = t.numel() * t.element_size()
+    st = getattr(_stage_tls, "bufs", None)
+    if st is None:
+        st = _stage_tls.bufs = {}
+    slot = st.get(dev)
+    if slot is not None and slot[1] is not None:
+        slot[1].synchronize()  # the H2D copy that last read this staging buffer
+    if slot is None or slot[0].numel() < nbytes:
+        slot = [torch.empty(int(nbytes * 1.25), dtype=torch.uint8, pin_memory=True), None]
+        st[dev] = slot
+    _lib.check(_lib.lib().ugs_host_copy(slot[0].data_ptr(), t.data_ptr(), nbytes, _host_threads()))
+    d = torch.empty(t.shape, dtype=t.dtype, device=dev)
+    d.copy_(slot[0][:nbytes].view(t.dtype).view(t.shape), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot[1] = ev
+    return d
+
+
 def _wire_emit_wanted(G: int, m: int, k: int, E: int) -> bool:
     """Large results for a CPU caller: emit the edges in the transfer format (no int64 copy of them in HBM, no packing
     pass). UGS_B200_WIRE_EMIT=0 keeps the int64 emission + packing; the size test mirrors _PACKED_MIN_BYTES with the
@@ -334,8 +367,8 @@ def sample_batch(edge_index: torch.Tensor, ptr: torch.Tensor, m_per_graph: int, 
     else:
         pb = [int(ptr[0]), int(ptr[-1])] if ptr.numel() > 1 else [0, 0]
     with torch.cuda.device(dev):
-        ei = edge_index.to(dev, non_blocking=True)
-        p = ptr.to(dev, non_blocking=True)
+        ei = _to_device(edge_index, dev)
+        p = _to_device(ptr, dev)
         # UGS_B200_VARIANT=uniform selects the exact-uniform accept/reject mode; default = reference law
         variant = os.environ.get("UGS_B200_VARIANT", "ref").lower()
         r = None

@@ -205,6 +205,20 @@ def test_host_widening_variants_equal_numpy():
     assert L.ugs_host_isa().decode() in ("scalar", "avx2", "avx512")
 
 
+def test_host_copy_is_a_parallel_memcpy():
+    """ugs_host_copy (pageable input -> pinned staging buffer, csrc/ugs_hostdeliver.cpp): every byte, at sizes around the
+    per-thread slice boundaries, with one thread and with more threads than slices."""
+    from ugs_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 4095, 4096, 4097, (1 << 20) - 1, (1 << 20) + 1, 5 * (1 << 20) + 123):
+        src = rng.integers(0, 256, size=n, dtype=np.uint8)
+        for threads in (1, 3, 16):
+            buf = np.full(n + 64, 7, np.uint8)
+            assert L.ugs_host_copy(buf[32:].ctypes.data, src.ctypes.data if n else buf.ctypes.data, n, threads) == 0
+            assert np.array_equal(buf[32:32 + n], src) and (buf[:32] == 7).all() and (buf[32 + n:] == 7).all()
+
+
 def test_host_store_bandwidth_probe_and_pool():
     """The host-side roofline probe runs on the persistent worker pool (no GPU needed) and is re-entrant from threads."""
     import ctypes

@@ -299,6 +299,29 @@ def test_wire_emission_equals_plain_copy(cuda_lib, k, m, monkeypatch):
     assert all(torch.equal(a, b) for a, b in zip(mixed, plain2))
 
 
+def test_large_pageable_inputs_are_staged_by_host_threads(cuda_lib, monkeypatch):
+    """The trainer hands over pageable `.cpu()` tensors (experiment.py:877-878): above 32 MB they reach the device through a
+    cached pinned staging buffer filled by the delivery's host threads (ugs_host_copy). Same results as with pinned
+    inputs, call after call (the staging buffer is reused), also for a non-contiguous edge_index (plain copy)."""
+    import ugs_sampler
+    from ugs_b200 import synth
+    monkeypatch.setattr(ugs_sampler, "_STAGE_MIN_BYTES", 1 << 20)
+    ei, ptr = synth.make_batch("zinc", 6000, seed=3)
+    assert ei.nbytes > ugs_sampler._STAGE_MIN_BYTES
+    pinned = ugs_sampler.sample_batch(torch.from_numpy(ei).pin_memory(), torch.from_numpy(ptr).pin_memory(), 4, 5, "sample", 9)
+    for rep in range(3):
+        got = ugs_sampler.sample_batch(torch.from_numpy(ei.copy()), torch.from_numpy(ptr.copy()), 4, 5, "sample", 9)
+        assert all(torch.equal(a, b) for a, b in zip(got, pinned))
+    ei2, ptr2 = synth.make_batch("zinc", 7000, seed=4)   # a larger one: the staging buffer grows
+    a = ugs_sampler.sample_batch(torch.from_numpy(ei2), torch.from_numpy(ptr2), 3, 4, "sample", 1)
+    b = ugs_sampler.sample_batch(torch.from_numpy(ei2).pin_memory(), torch.from_numpy(ptr2).pin_memory(), 3, 4, "sample", 1)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    strided = torch.from_numpy(np.ascontiguousarray(ei.T)).t()   # [2, E] view of an [E, 2] array
+    assert not strided.is_contiguous()
+    c = ugs_sampler.sample_batch(strided, torch.from_numpy(ptr), 4, 5, "sample", 9)
+    assert all(torch.equal(x, y) for x, y in zip(c, pinned))
+
+
 def test_concurrent_calls_from_python_threads(cuda_lib, monkeypatch):
     """ctypes releases the GIL, so two Python threads can be inside libugs_b200 at the same time (the reference holds
     the GIL for the whole call): results must be the ones of the serial calls."""
