@@ -344,7 +344,7 @@ k_sample_small_pipe(const i64* __restrict__ ptr, int G, i64 node_base, i64 m, in
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     PipeWarp& pw = sm_all[warp];
-#define W ((int)gridDim.x * SAMP_WARPS)
+    const int W = (int)gridDim.x * SAMP_WARPS;  // graphs are dealt round-robin to the grid's warps
     int g = (int)blockIdx.x * SAMP_WARPS + warp;
     if (g >= G) return;
     const int ntiles = (int)((m + 31) >> 5);
@@ -415,7 +415,6 @@ k_sample_small_pipe(const i64* __restrict__ ptr, int G, i64 node_base, i64 m, in
         slot = slot1;
         buf ^= 1;
     }
-#undef W
 }
 
 // m <= 16 samples per graph (QM9-style completeness runs: m = 10) leave most lanes of a (graph, 32-sample tile) warp
