@@ -232,7 +232,7 @@ static long long wire_chunk_bytes() {
     if (!v) {
         const char* e = getenv("UGS_B200_WIRE_CHUNK_MB");
         long long mb = e ? atoll(e) : 0;
-        if (mb < 1 || mb > 1024) mb = 32;
+        if (mb < 1 || mb > 1024) mb = 8;  // measured (profiles/r02_chunk_sweep.txt): 1 MB 54.4 ms, 4-8 MB 50.6, 32 MB 52.2, 64 MB 53.3
         v = mb << 20;
     }
     return v;
