@@ -427,11 +427,12 @@ int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* e
  * ugs_deliver_outputs_wire then packs only the node ids and runs the copy / widen pipeline (dma_fraction 0). Replaces the
  * same reference lines as ugs_emit_edges + ugs_deliver_outputs (sampler.cpp:205-280, :190;
  * ugs_sampler_batch_extension.cpp:95,257-290). wire_bytes >= ugs_deliver_wire_bytes(G * m, k, total, 1), same value in
- * both calls. UGS_ELIMIT from the delivery: a delta does not fit 16 bits -- the caller emits the int64 arrays
+ * both calls. n_general (the batch's count of general-path graphs) must be 0 (UGS_ELIMIT otherwise). UGS_ELIMIT from the delivery: a delta does not fit 16 bits -- the caller emits the int64 arrays
  * (ugs_emit_edges_packed) and delivers them with ugs_deliver_outputs. */
-int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, const void* workspace,
-                        const ugs_layout* L, const int64_t* nodes, const int64_t* edge_ptr, int64_t total, void* d_wire,
-                        size_t wire_bytes, const void* sample_scratch, size_t sample_scratch_bytes, void* stream);
+int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
+                        const void* workspace, const ugs_layout* L, const int64_t* nodes, const int64_t* edge_ptr,
+                        int64_t total, void* d_wire, size_t wire_bytes, const void* sample_scratch,
+                        size_t sample_scratch_bytes, void* stream);
 int ugs_deliver_outputs_wire(const int64_t* nodes, int64_t B, int k, int64_t total, void* d_wire, void* h_wire,
                              size_t wire_bytes, int64_t* h_nodes, int64_t* h_edge_index, int64_t* h_edge_src,
                              int n_threads, int64_t* h_stats, void* stream);

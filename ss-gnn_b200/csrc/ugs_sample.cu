@@ -1869,12 +1869,14 @@ extern "C" int ugs_emit_edges_packed(const int64_t* ptr, int64_t G, int64_t node
                                edge_index_out, edge_src_out, sample_scratch, sample_scratch_bytes, 0, stream_);
 }
 
-extern "C" int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k,
+extern "C" int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
                                    const void* workspace, const ugs_layout* L, const int64_t* nodes,
                                    const int64_t* edge_ptr, int64_t total, void* d_wire, size_t wire_bytes,
                                    const void* sample_scratch, size_t sample_scratch_bytes, void* stream_) {
     if (!workspace || !L || !edge_ptr || !nodes || !d_wire) return ugs_set_error(UGS_EINVAL, "NULL argument");
     if (k < 1 || k > 8) return ugs_set_error(UGS_ELIMIT, "the wire emission needs k <= 8");
+    if (n_general != 0) return ugs_set_error(UGS_ELIMIT, "the wire emission covers bitmask-path graphs only (n_general = %lld)",
+                                             (long long)n_general);
     if (G <= 0 || m <= 0 || total <= 0) return UGS_OK;
     const UgsWire wl = ugs_wire_layout((size_t)(G * m) * (size_t)k, (size_t)total, (size_t)total, 1, 1);
     if (wire_bytes < wl.total) return ugs_set_error(UGS_EINVAL, "wire buffer too small");

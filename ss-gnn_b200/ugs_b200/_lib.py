@@ -142,7 +142,7 @@ def lib():
     L.ugs_deliver_wire_bytes.restype = sz
     L.ugs_deliver_wire_bytes.argtypes = [i64, ci, i64, ci]
     L.ugs_deliver_outputs.argtypes = [vp, i64, ci, vp, vp, i64, ci, cd, vp, vp, sz, vp, vp, vp, ci, vp, vp]
-    L.ugs_emit_edges_wire.argtypes = [vp, i64, i64, i64, ci, vp, LP, vp, vp, i64, vp, sz, vp, sz, vp]
+    L.ugs_emit_edges_wire.argtypes = [vp, i64, i64, i64, ci, i64, vp, LP, vp, vp, i64, vp, sz, vp, sz, vp]
     L.ugs_deliver_outputs_wire.argtypes = [vp, i64, ci, i64, vp, vp, sz, vp, vp, vp, ci, vp, vp]
     L.ugs_host_copy.argtypes = [vp, vp, sz, ci]
     L.ugs_host_store_bandwidth.restype = cd

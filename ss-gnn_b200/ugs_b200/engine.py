@@ -270,7 +270,7 @@ class DeviceBatch:
         G = max(self.G, 0)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ugs_emit_edges_wire(
-                _ptr(self.ptr), G, self.node_base, m, k, _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes),
+                _ptr(self.ptr), G, self.node_base, m, k, self.n_general, _ptr(self.ws), ctypes.byref(self.layout), _ptr(nodes),
                 _ptr(edge_ptr), total, _ptr(d_wire), int(d_wire.numel()), _ptr(scratch), sbytes, _stream()))
 
     def emit_last(self, mode: str = "sample"):
