@@ -198,7 +198,7 @@ __device__ __forceinline__ void sample_tiles_staged(const TabT& s, const unsigne
             // the row of lane i starts at byte (s0 + i) * 8k: 16-byte aligned for even k; a warp's rows are contiguous
             if (active) {
                 longlong2* out = reinterpret_cast<longlong2*>(nodes_out + (s0 + lane) * KT);
-                if (((nlo >> (8 * (KT - 1))) & 0xFFull) != 0xFFull) {  // complete row: the last entry is set, so all are
+                if (((nlo >> (8 * (KT > 0 ? KT - 1 : 0))) & 0xFFull) != 0xFFull) {  // complete row: the last entry is set, so all are
 #pragma unroll
                     for (int q = 0; q < KT / 2; ++q)
                         out[q] = make_longlong2(lo + (i64)((u32)(nlo >> (16 * q)) & 0xFFu),
