@@ -422,12 +422,12 @@ int ugs_deliver_outputs(const int64_t* nodes, int64_t B, int k, const int64_t* e
                         void* stream);
 /* The same delivery without an int64 copy of the edges in HBM (mode "sample", k <= 8, graph-contiguous columns, no
  * general-path graph -- the ZINC-shaped headline batch): ugs_emit_edges_wire is the emission pass of ugs_emit_edges_packed
- * writing the transfer format straight into d_wire (one byte j | l << 4 per entry; the source column as a 16-bit delta
- * against the first column of the graph that owns its 4096-entry block), 3 instead of 24 bytes per entry;
+ * writing the transfer format straight into d_wire (one byte j | l << 4 per entry; the source column as an 8-bit delta
+ * against the first column of the graph that owns its 1024-entry block), 2 instead of 24 bytes per entry;
  * ugs_deliver_outputs_wire then packs only the node ids and runs the copy / widen pipeline (dma_fraction 0). Replaces the
  * same reference lines as ugs_emit_edges + ugs_deliver_outputs (sampler.cpp:205-280, :190;
  * ugs_sampler_batch_extension.cpp:95,257-290). wire_bytes >= ugs_deliver_wire_bytes(G * m, k, total, 1), same value in
- * both calls. n_general (the batch's count of general-path graphs) must be 0 (UGS_ELIMIT otherwise). UGS_ELIMIT from the delivery: a delta does not fit 16 bits -- the caller emits the int64 arrays
+ * both calls. n_general (the batch's count of general-path graphs) must be 0 (UGS_ELIMIT otherwise). UGS_ELIMIT from the delivery: a delta does not fit its 8 / 16 bits -- the caller emits the int64 arrays
  * (ugs_emit_edges_packed) and delivers them with ugs_deliver_outputs. */
 int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_base, int64_t m, int k, int64_t n_general,
                         const void* workspace, const ugs_layout* L, const int64_t* nodes, const int64_t* edge_ptr,

@@ -37,14 +37,16 @@ typedef int32_t i32;
 
 // ---- widening kernels ---------------------------------------------------------------------------------------------
 // kind 0: int32 -> int64; kind 1: low nibble of a byte -> int64; kind 2: high nibble -> int64;
-// kind 3: 16-bit delta + base -> int64 (0xFFFF -> -1), one base per call (the caller splits at block boundaries)
+// kind 3: 16-bit delta + base -> int64 (0xFFFF -> -1), one base per call (the caller splits at block boundaries);
+// kind 4: 8-bit delta + base -> int64 (0xFF -> -1), likewise
 static inline void st64(i64* p, i64 v) { _mm_stream_si64((long long*)p, (long long)v); }
 
 static void widen_scalar(int kind, const void* src, i64* dst, size_t n, i64 base) {
     if (kind == 0) { const i32* s = (const i32*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, (i64)s[i]); }
     else if (kind == 1) { const uint8_t* s = (const uint8_t*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, (i64)(s[i] & 15u)); }
     else if (kind == 2) { const uint8_t* s = (const uint8_t*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, (i64)(s[i] >> 4)); }
-    else { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, s[i] == 0xFFFFu ? (i64)-1 : base + (i64)s[i]); }
+    else if (kind == 3) { const uint16_t* s = (const uint16_t*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, s[i] == 0xFFFFu ? (i64)-1 : base + (i64)s[i]); }
+    else { const uint8_t* s = (const uint8_t*)src; for (size_t i = 0; i < n; ++i) st64(dst + i, s[i] == 0xFFu ? (i64)-1 : base + (i64)s[i]); }
 }
 
 __attribute__((target("avx2"))) static void widen_avx2(int kind, const void* src, i64* dst, size_t n, i64 base) {
@@ -54,11 +56,17 @@ __attribute__((target("avx2"))) static void widen_avx2(int kind, const void* src
     widen_scalar(kind, src, dst, h, base);
     i = h;
     const __m256i vbase = _mm256_set1_epi64x(base), vm1 = _mm256_set1_epi64x(-1), vff = _mm256_set1_epi64x(0xFFFF);
+    const __m256i vf8 = _mm256_set1_epi64x(0xFF);
     const __m128i nib = _mm_set1_epi8(15);
     for (; i + 4 <= n; i += 4) {
         __m256i v;
         if (kind == 0) v = _mm256_cvtepi32_epi64(_mm_loadu_si128((const __m128i*)((const i32*)src + i)));
-        else if (kind == 1 || kind == 2) {
+        else if (kind == 4) {
+            uint32_t w;
+            memcpy(&w, (const uint8_t*)src + i, 4);
+            const __m256i d = _mm256_cvtepu8_epi64(_mm_cvtsi32_si128((int)w));
+            v = _mm256_blendv_epi8(_mm256_add_epi64(d, vbase), vm1, _mm256_cmpeq_epi64(d, vf8));
+        } else if (kind == 1 || kind == 2) {
             uint32_t w;
             memcpy(&w, (const uint8_t*)src + i, 4);
             __m128i b = _mm_cvtsi32_si128((int)w);
@@ -83,11 +91,17 @@ __attribute__((target("avx512f"))) static void widen_avx512(int kind, const void
     widen_scalar(kind, src, dst, h, base);
     i = h;
     const __m512i vbase = _mm512_set1_epi64(base), vm1 = _mm512_set1_epi64(-1), vff = _mm512_set1_epi64(0xFFFF);
+    const __m512i vf8 = _mm512_set1_epi64(0xFF);
     const __m128i nib = _mm_set1_epi8(15);
     for (; i + 8 <= n; i += 8) {  // one full cache line per store: no read-for-ownership, no partial-line merging
         __m512i v;
         if (kind == 0) v = _mm512_cvtepi32_epi64(_mm256_loadu_si256((const __m256i*)((const i32*)src + i)));
-        else if (kind == 1 || kind == 2) {
+        else if (kind == 4) {
+            uint64_t w;
+            memcpy(&w, (const uint8_t*)src + i, 8);
+            const __m512i d = _mm512_cvtepu8_epi64(_mm_cvtsi64_si128((long long)w));
+            v = _mm512_mask_mov_epi64(_mm512_add_epi64(d, vbase), _mm512_cmpeq_epi64_mask(d, vf8), vm1);
+        } else if (kind == 1 || kind == 2) {
             uint64_t w;
             memcpy(&w, (const uint8_t*)src + i, 8);
             __m128i b = _mm_cvtsi64_si128((long long)w);
@@ -126,7 +140,7 @@ extern "C" int ugs_host_widen(int kind, const void* src, int64_t* dst, size_t n,
     widen_fn f = widen_scalar;
     if (isa && !strcmp(isa, "avx2")) { if (!__builtin_cpu_supports("avx2")) return -1; f = widen_avx2; }
     else if (isa && !strcmp(isa, "avx512")) { if (!__builtin_cpu_supports("avx512f")) return -1; f = widen_avx512; }
-    if (kind < 0 || kind > 3) return -2;
+    if (kind < 0 || kind > 4) return -2;
     f(kind, src, dst, n, base);
     _mm_sfence();
     return 0;
@@ -249,8 +263,9 @@ struct Item {
     const char* src;   // host wire address of element 0 of the item
     i64* dst;
     size_t n;          // elements
-    size_t first;      // kind 3: index of element 0 inside the packed part (block = first / 4096)
-    const i64* bases;  // kind 3
+    size_t first;      // kind 3 / 4: index of element 0 inside the packed part (block = first / blk)
+    const i64* bases;  // kind 3 / 4
+    size_t blk;        // kind 3: UGS_DELTA_BLOCK, kind 4: UGS_DELTA8_BLOCK
     cudaEvent_t ev;
 };
 struct DeliverCtx {
@@ -270,16 +285,17 @@ static void deliver_slice(void* ctx_, int t, int T) {
         const size_t per = ((it.n + T - 1) / T + 7) & ~(size_t)7;
         const size_t a = (size_t)t * per, b = (a + per < it.n) ? a + per : it.n;
         if (a >= b) continue;
-        if (it.kind != 3) {
+        if (it.kind != 3 && it.kind != 4) {
             const size_t esz = it.kind == 0 ? 4 : 1;
             c->fn(it.kind, it.src + a * esz, it.dst + a, b - a, 0);
-        } else {  // one base per 4096-value block
+        } else {  // one base per block of it.blk values
+            const size_t esz = it.kind == 3 ? 2 : 1;
             size_t i = a;
             while (i < b) {
-                const size_t blk = (it.first + i) / UGS_DELTA_BLOCK;
-                size_t end = (blk + 1) * UGS_DELTA_BLOCK - it.first;
+                const size_t blk = (it.first + i) / it.blk;
+                size_t end = (blk + 1) * it.blk - it.first;
                 if (end > b) end = b;
-                c->fn(3, it.src + i * 2, it.dst + i, end - i, it.bases[blk]);
+                c->fn(it.kind, it.src + i * esz, it.dst + i, end - i, it.bases[blk]);
                 i = end;
             }
         }
@@ -337,10 +353,11 @@ static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* e
     std::vector<cudaEvent_t> events;
     std::vector<Item> items;
     int delta16 = 1;
-    UgsWire w = ugs_wire_layout(pn, pe, pi, pairs_u8, 1);
+    UgsWire w = prepacked ? ugs_wire_layout_emit(pn, pe) : ugs_wire_layout(pn, pe, pi, pairs_u8, 1);
     if (pn + pe + pi > 0) {  // the int32 layout is the larger one: the buffers must hold it in case the deltas overflow
         if (!d_wire || !h_wire) return ugs_set_error(UGS_EINVAL, "NULL wire buffer");
-        if (wire_bytes < ugs_wire_layout(pn, pe, pi, pairs_u8, 0).total) return ugs_set_error(UGS_EINVAL, "wire buffer too small");
+        if (wire_bytes < (prepacked ? w.total : ugs_wire_layout(pn, pe, pi, pairs_u8, 0).total))
+            return ugs_set_error(UGS_EINVAL, "wire buffer too small");
     }
     char* hw = (char*)h_wire;
     char* dw = (char*)d_wire;
@@ -384,7 +401,7 @@ static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* e
             const unsigned long long* bad = (const unsigned long long*)(hw + w.bad);
             if (bad[1]) { rc = ugs_set_error(UGS_ELIMIT, "%llu edge entries do not fit the packed wire format", bad[1]); goto out; }
             if (prepacked && (bad[0] | bad[2])) {
-                rc = ugs_set_error(UGS_ELIMIT, "%llu node ids / %llu source columns do not fit a 16-bit delta", bad[0], bad[2]);
+                rc = ugs_set_error(UGS_ELIMIT, "%llu node ids do not fit a 16-bit / %llu source columns an 8-bit delta", bad[0], bad[2]);
                 goto out;
             }
             if (bad[0]) {  // some 4096-value block spreads over more than 65534: int32 for node ids / source columns
@@ -405,6 +422,7 @@ static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* e
                 Item it;
                 it.kind = kind; it.src = hw + off + a * esz; it.dst = dst + a; it.n = (n - a < per) ? n - a : per;
                 it.first = a; it.bases = (const i64*)(hw + bases_off); it.ev = nullptr;
+                it.blk = kind == 4 ? UGS_DELTA8_BLOCK : UGS_DELTA_BLOCK;
                 items.push_back(it);
                 if (twin_dst) { it.kind = 2; it.dst = twin_dst + a; items.push_back(it); }
             }
@@ -416,7 +434,8 @@ static int deliver_impl(const int64_t* nodes, int64_t B, int k, const int64_t* e
             add_region(0, w.ei, pi, 4, h_edge_index + si, 0);
             add_region(0, w.ei + pi * 4, pi, 4, h_edge_index + NE + si, 0);
         }
-        add_region(delta16 ? 3 : 0, w.src, pe, delta16 ? 2 : 4, h_edge_src + se, w.src_base);
+        if (prepacked) add_region(4, w.src, pe, 1, h_edge_src + se, w.src_base);
+        else add_region(delta16 ? 3 : 0, w.src, pe, delta16 ? 2 : 4, h_edge_src + se, w.src_base);
         add_region(delta16 ? 3 : 0, w.nodes, pn, delta16 ? 2 : 4, h_nodes + sn, w.nodes_base);
         const size_t ev0 = events.size();
         if (take_events(dev, ev0 + items.size(), events) != 0) { rc = ugs_set_error(UGS_ECUDA, "cudaEventCreate failed"); goto out; }

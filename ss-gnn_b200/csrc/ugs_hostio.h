@@ -34,6 +34,24 @@ static inline UgsWire ugs_wire_layout(size_t pn, size_t pe, size_t pi, int pairs
     return w;
 }
 
+// Layout of the wire buffer when the EMISSION pass writes the edge part itself (ugs_emit_edges_wire): node ids as in the
+// packed layout (16-bit deltas per 4096-value block), one byte (row0 | row1 << 4) per edge entry, and the source columns
+// as 8-BIT deltas against the base of their 1024-entry block (the first column of the graph that owns the block's first
+// entry: 1024 entries are half a ZINC-sized graph's samples, so a block spans two or three graphs' columns).
+#define UGS_DELTA8_BLOCK 1024
+static inline size_t ugs_delta8_blocks(size_t n) { return (n + UGS_DELTA8_BLOCK - 1) / UGS_DELTA8_BLOCK; }
+static inline UgsWire ugs_wire_layout_emit(size_t pn, size_t pe) {
+    UgsWire w;
+    w.nodes = 0;
+    w.src = ugs_align256(pn * 2);
+    w.ei = w.src + ugs_align256(pe);
+    w.nodes_base = w.ei + ugs_align256(pe);
+    w.src_base = w.nodes_base + ugs_align256(ugs_delta_blocks(pn) * 8);
+    w.bad = w.src_base + ugs_align256(ugs_delta8_blocks(pe) * 8);
+    w.total = w.bad + 256;
+    return w;
+}
+
 // Device side (ugs_hostio.cu): packs the given parts into d_wire according to *w; zeroes and fills the two counters.
 int ugs_pack_parts(const int64_t* nodes, size_t pn, const int64_t* ei_row0, const int64_t* ei_row1, size_t pi,
                    const int64_t* edge_src, size_t pe, int pairs_u8, int delta16, void* d_wire, const UgsWire* w,

@@ -1035,13 +1035,13 @@ struct __align__(16) SmallEmit<unsigned short> {  // 5664 bytes per warp: 5 CTAs
 // else  :                            staged entry = payload << 15 | lane << 10 | l << 5 | j  (32 bits)
 // Entries of the samples of tiles [t0, t1) of graph g, by one warp whose shared-memory slice is `s`.
 // WIRE (host delivery, ugs_emit_edges_wire): the flush writes the transfer format of csrc/ugs_hostio.h directly instead
-// of three int64 arrays -- one byte (j | l << 4) per entry and the source column as a 16-bit delta against bases[] of its
-// 4096-entry block (k_wire_src_bases) -- 3 instead of 24 bytes per entry, and no int64 copy of the edges in HBM at all.
+// of three int64 arrays -- one byte (j | l << 4) per entry and the source column as an 8-bit delta against bases[] of its
+// 1024-entry block (k_wire_src_bases) -- 2 instead of 24 bytes per entry, and no int64 copy of the edges in HBM at all.
 struct WireOut {
     unsigned char* ei;
-    unsigned short* src;
+    unsigned char* src;
     const i64* bases;
-    unsigned long long* bad;  // entries whose delta does not fit 16 bits (the caller falls back to the int64 path)
+    unsigned long long* bad;  // entries whose delta does not fit 8 bits (the caller falls back to the int64 path)
 };
 
 template <bool NARROW, bool WIRE = false>
@@ -1209,20 +1209,15 @@ __device__ __forceinline__ void emit_graph_tiles(
                     pu += 32; pv += 32; ps += 32; sg += 32;
                 }
             } else if (NARROW && WIRE) {
-                // a run (<= NIB_STAGE entries) touches at most two 4096-entry blocks
-                const i64 blk0 = base >> 12;
-                const int split = (int)(((blk0 + 1) << 12) - base);  // entries [split, run) belong to block blk0 + 1
-                const i64 rel0 = c0 - wo.bases[blk0];
-                const i64 rel1 = (split < run) ? c0 - wo.bases[blk0 + 1] : rel0;
                 unsigned char* pe8 = wo.ei + base;
-                unsigned short* ps16 = wo.src + base;
+                unsigned char* ps8 = wo.src + base;
                 int nbad = 0;
-                for (int e = lane; e < run; e += 32) {
+                for (int e = lane; e < run; e += 32) {  // 32 consecutive entries: one or two blocks, i.e. a broadcast load
                     const u32 pk = s.stage[e];
                     pe8[e] = (unsigned char)((pk & 7u) | (((pk >> 3) & 7u) << 4));
-                    const i64 d = (e < split ? rel0 : rel1) + (i64)(pk >> 6);
-                    if (d < 0 || d >= 0xFFFF) nbad++;
-                    ps16[e] = (unsigned short)d;
+                    const i64 d = c0 - wo.bases[(base + e) >> 10] + (i64)(pk >> 6);
+                    if (d < 0 || d >= 0xFF) nbad++;
+                    ps8[e] = (unsigned char)d;
                 }
                 if (nbad) atomicAdd(wo.bad, (unsigned long long)nbad);
             } else if (NARROW) {
@@ -1310,13 +1305,13 @@ k_emit_small(const i64* __restrict__ ptr, i64 G, i64 node_base, i64 m, int k, in
                                    out_v, out_src, packed, wo);
 }
 
-// bases[b] for the 16-bit source-column deltas of block b (entries [4096 b, 4096 b + 4096) of the output): the first
+// bases[b] for the 8-bit source-column deltas of block b (entries [1024 b, 1024 b + 1024) of the output): the first
 // column of the graph that owns the block's first entry. Every later entry of the block belongs to the same or a later
-// graph, so its source column is >= that base; k_emit_small<true, true> counts the entries whose delta exceeds 16 bits.
+// graph, so its source column is >= that base; k_emit_small<true, true> counts the entries whose delta exceeds 8 bits.
 __global__ void k_wire_src_bases(const i64* __restrict__ edge_ptr, i64 B, i64 m, i64 total, const i64* __restrict__ cstart,
                                  i64* __restrict__ bases) {
     const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    const i64 pos = b << 12;
+    const i64 pos = b << 10;  // UGS_DELTA8_BLOCK
     if (pos >= total) return;
     i64 lo = 0, hi = B;  // the last sample s with edge_ptr[s] <= pos (edge_ptr[0] = 0, edge_ptr[B] = total > pos)
     while (hi - lo > 1) {
@@ -1878,21 +1873,21 @@ extern "C" int ugs_emit_edges_wire(const int64_t* ptr, int64_t G, int64_t node_b
     if (n_general != 0) return ugs_set_error(UGS_ELIMIT, "the wire emission covers bitmask-path graphs only (n_general = %lld)",
                                              (long long)n_general);
     if (G <= 0 || m <= 0 || total <= 0) return UGS_OK;
-    const UgsWire wl = ugs_wire_layout((size_t)(G * m) * (size_t)k, (size_t)total, (size_t)total, 1, 1);
+    const UgsWire wl = ugs_wire_layout_emit((size_t)(G * m) * (size_t)k, (size_t)total);
     if (wire_bytes < wl.total) return ugs_set_error(UGS_EINVAL, "wire buffer too small");
     cudaStream_t st = (cudaStream_t)stream_;
     WS w = ws_views(const_cast<void*>(workspace), L);
     char* base = (char*)d_wire;
     WireOut wo;
     wo.ei = (unsigned char*)(base + wl.ei);
-    wo.src = (unsigned short*)(base + wl.src);
+    wo.src = (unsigned char*)(base + wl.src);
     wo.bases = (const i64*)(base + wl.src_base);
     wo.bad = (unsigned long long*)(base + wl.bad) + 2;  // behind the two counters of ugs_pack_parts
     UGS_CUDA_CHECK(cudaMemsetAsync(wo.bad, 0, 8, st));
     const u64* packed = nullptr;
     if (sample_scratch && sample_scratch_bytes >= ugs_sample_scratch_bytes(G, m))
         packed = reinterpret_cast<const u64*>((const char*)sample_scratch + packed_rows_offset(G * m));
-    const int64_t nblk = (total + 4095) >> 12;
+    const int64_t nblk = (int64_t)ugs_delta8_blocks((size_t)total);
     k_wire_src_bases<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(edge_ptr, G * m, m, total, w.cstart, (i64*)(base + wl.src_base));
     UGS_LAUNCH_CHECK("k_wire_src_bases");
     int tpi; int64_t ipg;

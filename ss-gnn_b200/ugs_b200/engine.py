@@ -259,8 +259,13 @@ class DeviceBatch:
         """True if the rows of the last `sample(..., emit=False)` call can be emitted in the host-transfer format
         (`emit_last_wire`): mode "sample", k <= 8, graph-contiguous columns, no general-path graph, reference law."""
         a = self._emit_args
-        return (a is not None and mode == "sample" and a[4] <= 8 and self.perm is None and self.n_general == 0
-                and a[7] is not None and a[2] > 0)
+        if not (a is not None and mode == "sample" and a[4] <= 8 and self.perm is None and self.n_general == 0
+                and a[7] is not None and a[2] > 0):
+            return False
+        # the 8-bit source-column deltas need every 1024-entry block of the output to span fewer than 255 columns: with
+        # at least 1024 entries per sampled graph a block covers two graphs (the delivery reports an overflow and the
+        # caller takes the int64 emission, so this is only about not wasting an emission pass)
+        return a[2] >= 1024 * max(self.G - self.n_skipped, 1)
 
     def emit_last_wire(self, d_wire: torch.Tensor):
         """Induced-edge emission of the last `sample(..., emit=False)` call straight into the transfer format of the host

@@ -216,8 +216,9 @@ def _deliver_wire(b, outs, stats, k: int):
             return None
         _lib.check(rc)
     _to_host_batch.last_d2h_bytes = int(st[0]) + 8 * (eptr.numel() + sptr.numel())
-    _to_host_batch.last_delivery = (f"dma_fraction 0.00: 0 B as int64 by DMA + {int(st[0])} B packed (16-bit deltas / u8 pairs, "
-                                    f"edges emitted in the wire format), widened by {threads} host threads")
+    _to_host_batch.last_delivery = (f"dma_fraction 0.00: 0 B as int64 by DMA + {int(st[0])} B packed (node ids: 16-bit deltas; "
+                                    f"edges emitted in the wire format: u8 pairs + 8-bit source-column deltas), widened by "
+                                    f"{threads} host threads")
     return [h_nodes, h_eidx, h_eptr, h_sptr, h_esrc]
 
 

@@ -179,8 +179,13 @@ def test_host_widening_variants_equal_numpy():
     for isa in (b"scalar", b"avx2", b"avx512"):
         for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4099):
             for shift in (0, 1, 3, 5):
-                for kind in (0, 1, 2, 3):
-                    if kind == 0:
+                for kind in (0, 1, 2, 3, 4):
+                    if kind == 4:
+                        src = rng.integers(0, 256, size=n, dtype=np.int64).astype(np.uint8)
+                        if n:
+                            src[rng.integers(0, n, size=max(1, n // 5))] = 0xFF
+                        want = np.where(src == 0xFF, -1, 10 ** 12 + src.astype(np.int64))
+                    elif kind == 0:
                         src = rng.integers(-2 ** 31, 2 ** 31, size=n, dtype=np.int64).astype(np.int32)
                         want = src.astype(np.int64)
                     elif kind in (1, 2):
@@ -194,7 +199,7 @@ def test_host_widening_variants_equal_numpy():
                     buf = np.full(n + 16, -7, np.int64)
                     dst = buf[shift:shift + n]
                     rc = L.ugs_host_widen(kind, src.ctypes.data if n else None, dst.ctypes.data, n,
-                                          10 ** 12 if kind == 3 else 0, isa)
+                                          10 ** 12 if kind >= 3 else 0, isa)
                     if rc == -1:
                         continue
                     assert rc == 0

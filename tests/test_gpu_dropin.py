@@ -260,10 +260,10 @@ def test_packed_host_delivery_equals_plain_copy(cuda_lib, mode, monkeypatch):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
-@pytest.mark.parametrize("k,m", [(8, 37), (4, 70), (5, 17)])
-def test_wire_emission_equals_plain_copy(cuda_lib, k, m, monkeypatch):
+@pytest.mark.parametrize("k,m,wire_expected", [(8, 37, True), (6, 64, True), (5, 17, False)])
+def test_wire_emission_equals_plain_copy(cuda_lib, k, m, wire_expected, monkeypatch):
     """Large CPU results in mode "sample" with k <= 8: the emission pass writes the host-transfer format itself
-    (ugs_emit_edges_wire: one byte per entry, 16-bit source-column deltas against per-block graph bases) and
+    (ugs_emit_edges_wire: one byte per entry, 8-bit source-column deltas against per-block graph bases) and
     ugs_deliver_outputs_wire widens it -- bit-identical to the int64 emission + plain copy. Batches with skipped graphs,
     multi-edges / self loops and graphs above 32 vertices in between; a batch with a general-path graph and
     UGS_B200_WIRE_EMIT=0 take the int64 emission."""
@@ -272,7 +272,8 @@ def test_wire_emission_equals_plain_copy(cuda_lib, k, m, monkeypatch):
     monkeypatch.setattr(ugs_sampler, "_PACKED_MIN_BYTES", 0)
     monkeypatch.setattr(ugs_sampler._engine, "fused_eligible", lambda *a: False)  # the staged path, as for large batches
     rng = np.random.default_rng(3 * k + m)
-    parts = [synth.make_batch("zinc", 1500, seed=k), random_batch(rng, 40, 1, 45, deg=2.5, weird=True),
+    # molecules, graphs smaller than k in between (no entries: the next graph's columns start further away)
+    parts = [synth.make_batch("zinc", 1500, seed=k), random_batch(rng, 25, 1, 3, deg=1.0),
              synth.make_batch("qm9", 700, seed=m)]
     ei, ptr = synth.concat_batches(parts)
     tei, tptr = torch.from_numpy(ei), torch.from_numpy(ptr)
@@ -280,15 +281,34 @@ def test_wire_emission_equals_plain_copy(cuda_lib, k, m, monkeypatch):
     plain = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
     monkeypatch.delenv("UGS_B200_PACKED_D2H")
     wire = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
-    assert "emitted in the wire format" in ugs_sampler._to_host_batch.last_delivery
+    # few entries per graph (k = 5, m = 17): a 1024-entry block would span many graphs' columns, the int64 emission is taken
+    assert ("emitted in the wire format" in ugs_sampler._to_host_batch.last_delivery) == wire_expected
     for a, b in zip(wire, plain):
         assert a.dtype == torch.int64 and a.is_pinned() and torch.equal(a, b)
     assert ugs_sampler.sample_batch.last_stats["n_edge_entries"] == plain[4].numel()
+    # multigraphs with hundreds of columns between the molecules: wherever a 1024-entry block spans more than 254 columns
+    # the delivery reports it and the call takes the int64 emission; either way the result is the plain copy's
+    parts.insert(1, random_batch(rng, 40, 1, 45, deg=2.5, weird=True))
+    ei_w, ptr_w = synth.concat_batches(parts)
+    monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+    plain_w = ugs_sampler.sample_batch(torch.from_numpy(ei_w), torch.from_numpy(ptr_w), m, k, "sample", 13)
+    monkeypatch.delenv("UGS_B200_PACKED_D2H")
+    got_w = ugs_sampler.sample_batch(torch.from_numpy(ei_w), torch.from_numpy(ptr_w), m, k, "sample", 13)
+    assert all(torch.equal(a, b) for a, b in zip(got_w, plain_w))
     monkeypatch.setenv("UGS_B200_WIRE_EMIT", "0")
     classic = ugs_sampler.sample_batch(tei, tptr, m, k, "sample", 11)
     assert "emitted in the wire format" not in ugs_sampler._to_host_batch.last_delivery
     monkeypatch.delenv("UGS_B200_WIRE_EMIT")
     assert all(torch.equal(a, b) for a, b in zip(classic, plain))
+    # graphs of 55-64 vertices with up to 320 columns each and thousands of entries per graph: eligible by the entry count,
+    # but a 1024-entry block spans more than 254 columns -> the delivery reports it, the int64 emission takes over
+    ei_d, ptr_d = random_batch(rng, 200, 55, 64, deg=2.5, weird=False)
+    monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
+    plain_d = ugs_sampler.sample_batch(torch.from_numpy(ei_d), torch.from_numpy(ptr_d), 64, k, "sample", 14)
+    monkeypatch.delenv("UGS_B200_PACKED_D2H")
+    got_d = ugs_sampler.sample_batch(torch.from_numpy(ei_d), torch.from_numpy(ptr_d), 64, k, "sample", 14)
+    assert "emitted in the wire format" not in ugs_sampler._to_host_batch.last_delivery
+    assert all(torch.equal(a, b) for a, b in zip(got_d, plain_d))
     # one general-path graph (70 vertices) in the batch: not eligible, the int64 path delivers
     ei2, ptr2 = synth.concat_batches(parts + [random_batch(rng, 3, 1, 30, deg=2.5, big=[(1, 70)])])
     monkeypatch.setenv("UGS_B200_PACKED_D2H", "0")
