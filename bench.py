@@ -634,9 +634,10 @@ def main():
                "host_peak_source": "ugs_host_store_bandwidth: 1 GiB of non-temporal stores per rank with the delivery's "
                                    "thread count, all ranks at the same time, sum over ranks",
                "api": "ugs_sampler.sample_batch(cpu int64 tensors) -> pinned cpu int64 tensors; results cross PCIe packed "
-                      "(16-bit deltas per 4096-value block for node ids / source columns, one byte per edge entry) and are "
-                      "widened by a persistent pool of host threads (AVX-512 / AVX2 non-temporal stores) while the copy "
-                      "runs; bound by host memory bandwidth: host_gbs vs host_peak_gbs"}
+                      "(node ids as 16-bit deltas per 4096-value block; edge entries emitted by the emission kernel itself as "
+                      "one byte of index pair + an 8-bit source-column delta per 1024-entry block) and are widened by a "
+                      "persistent pool of host threads (AVX-512 / AVX2 non-temporal stores) while the copy runs; bound by the "
+                      "host memory system: host_gbs vs host_peak_gbs"}
         del outs
 
     if rank == 0:
